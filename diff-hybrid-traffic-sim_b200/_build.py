@@ -1,0 +1,68 @@
+"""Builds libdhts_b200.so (hand-written sm_100a CUDA + the C ABI of include/dhts.h) in-tree with nvcc."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+SO = os.path.join(_HERE, "libdhts_b200.so")
+SOURCES = ["arz_kernels.cu", "idm_kernels.cu", "convert_kernels.cu", "capi_misc.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
+              "-Xcompiler", "-fvisibility=hidden"]
+
+
+def _nvcc() -> str:
+    for c in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if c and os.path.exists(c):
+            return c
+    raise RuntimeError("nvcc not found; libdhts_b200.so cannot be built")
+
+
+def _stale() -> bool:
+    if not os.path.exists(SO):
+        return True
+    t = os.path.getmtime(SO)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(os.path.dirname(_HERE), "include", "dhts.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not _stale():
+        return SO
+    nvcc = _nvcc()
+    objdir = os.path.join(_HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    env = dict(os.environ)
+    # $CC/$CXX in this image point at a gcc without a matching libstdc++ setup for nvcc; use the system one
+    if os.path.exists("/usr/bin/g++"):
+        ccbin = ["-ccbin", "/usr/bin/g++"]
+    else:
+        ccbin = []
+    objs = []
+    procs = []
+    for src in SOURCES:
+        path = os.path.join(CSRC, src)
+        if not os.path.exists(path):
+            continue
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        objs.append(obj)
+        cmd = [nvcc] + ccbin + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)))
+    for cmd, p in procs:
+        out, _ = p.communicate()
+        if verbose and out:
+            print(out)
+        if p.returncode != 0:
+            raise RuntimeError("nvcc failed: %s\n%s" % (" ".join(cmd), out))
+    cmd = [nvcc] + ccbin + ["-shared", "-o", SO] + objs + ["-lcudart"]
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    if r.returncode != 0:
+        raise RuntimeError("link failed: %s\n%s%s" % (" ".join(cmd), r.stdout, r.stderr))
+    return SO
+
+
+if __name__ == "__main__":
+    import sys
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

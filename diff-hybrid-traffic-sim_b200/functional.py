@@ -1,0 +1,104 @@
+"""Batched, device-resident API of the simulation step.
+
+Each function states which reference loop it stands for.  Tensors are CUDA
+tensors (float64 or float32); everything differentiates through the hand-written
+adjoint kernels.  Shapes: B macro lanes x N cells; V vehicles in L micro lanes
+(CSR ``lane_off``).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .ops import (EPSILON, ArzRolloutFn, ArzStepFn, IdmRolloutFn, IdmStepFn, MacroToMicroFn, MicroToMacroFn,
+                  csr_expand)
+
+
+def u_eq(r: torch.Tensor, umax) -> torch.Tensor:
+    """ARZ.compute_u_eq (model/macro/_arz.py:133-138), gamma = 0.5; differentiated by autograd like the reference's 0-dim ops."""
+    return umax * (1.0 - torch.sqrt(torch.clamp(r, min=0.0) + EPSILON))
+
+
+def compute_y(r: torch.Tensor, u: torch.Tensor, umax) -> torch.Tensor:
+    """ARZ.compute_y (model/macro/_arz.py:121-124)."""
+    return r * (u - u_eq(r, umax))
+
+
+def _per_lane(x, B, like: torch.Tensor) -> torch.Tensor:
+    t = torch.as_tensor(x, dtype=like.dtype, device=like.device)
+    return t.expand(B).contiguous() if t.dim() == 0 else t.contiguous()
+
+
+def arz_step(r_pad, y_pad, u_pad, dx, umax, dt, flags, ueq_pad=None, want_case=False):
+    """One Godunov step of B lanes: the batched dMacroForwardLayer.apply (dmacro_lane.py:83)
+    followed by set_next_state_vector_y's u (``_macro_lane.py:282-299``).
+    Inputs are padded [B, N+2] (ghost, cells, ghost); returns (nr, ny, nu)[B, N] (+ case [B, N+1])."""
+    B = r_pad.shape[0]
+    dx = _per_lane(dx, B, r_pad); umax = _per_lane(umax, B, r_pad)
+    return ArzStepFn.apply(r_pad, y_pad, u_pad.detach(), None if ueq_pad is None else ueq_pad.detach(), dx, umax, dt,
+                           flags.t, want_case)
+
+
+def arz_rollout(r0, u0, ghost_r, ghost_u, dx, umax, dt, steps, ckpt_every=32, flags=None):
+    """`steps` x RoadNetwork.forward over B disconnected dMacroLanes with static ghost cells, i.e. the
+    loop of example/inverse/_inverse.py:91-99 for example/inverse/macro.py, batched:
+    set_state_vector_u(r0, u0) -> steps x (boundary, forward, update_state) -> get_state_vector().
+    r0, u0 [B, N]; ghost_r, ghost_u [B, 2] (left, right).  Returns (rT, yT, uT) [B, N]."""
+    B, N = r0.shape
+    flags = flags or _lib.Flags(r0.device)
+    dxl = _per_lane(dx, B, r0); uml = _per_lane(umax, B, r0)
+    um = uml[:, None]
+    y0 = compute_y(r0, u0, um)                       # set_r_u, _arz.py:82-86 (autograd, true derivative)
+    ghost = torch.stack([ghost_r, compute_y(ghost_r, ghost_u, um), ghost_u.detach()], dim=-1)   # from_r_u, :74-80
+    try:
+        return ArzRolloutFn.apply(r0, y0, u0.detach(), ghost, dxl, uml, dt, steps, ckpt_every, flags.t)
+    except _lib.UnsupportedShape:
+        pass
+    # lane too long for the smem-resident kernel: chain the tiled per-step kernels (still CUDA)
+    r, y, u = r0, y0, u0.detach()
+    g = ghost
+    for _ in range(int(steps)):
+        r_pad = torch.cat([g[:, 0:1, 0], r, g[:, 1:2, 0]], dim=1)
+        y_pad = torch.cat([g[:, 0:1, 1], y, g[:, 1:2, 1]], dim=1)
+        u_pad = torch.cat([g[:, 0:1, 2], u.detach(), g[:, 1:2, 2]], dim=1)
+        r, y, u = ArzStepFn.apply(r_pad, y_pad, u_pad, None, dxl, uml, dt, flags.t, False)
+    return r, y, u
+
+
+def idm_step(p, v, params, lane_off, head, dt, flags, veh_lane=None, want_flags=False):
+    """One IDM step of all lanes: the batched dMicroForwardLayer.apply (dmicro_lane.py:75).
+    Returns (np, nv)[V] (+ per-vehicle clip / collision bits)."""
+    if veh_lane is None:
+        veh_lane = csr_expand(lane_off, p.numel())
+    return IdmStepFn.apply(p, v, head, params, lane_off, veh_lane, dt, flags.t, want_flags)
+
+
+def idm_rollout(p0, v0, params, lane_off, head, dt, steps, ckpt_every=32, flags=None, max_lane=None):
+    """`steps` x RoadNetwork.forward over L independent dMicroLanes whose heads follow the ghost leader
+    (head_position_delta, head_speed_delta): the loop of example/inverse/_inverse.py:91-99 for
+    example/inverse/micro.py, batched.  Returns (pT, vT) [V]."""
+    flags = flags or _lib.Flags(p0.device)
+    if max_lane is None:
+        max_lane = int((lane_off[1:] - lane_off[:-1]).max().item()) if lane_off.numel() > 1 else 0
+    try:
+        return IdmRolloutFn.apply(p0, v0, head, params, lane_off, max_lane, dt, steps, ckpt_every, flags.t)
+    except _lib.UnsupportedShape:
+        pass
+    veh_lane = csr_expand(lane_off, p0.numel())
+    p, v = p0, v0
+    for _ in range(int(steps)):
+        p, v = IdmStepFn.apply(p, v, head, params, lane_off, veh_lane, dt, flags.t, False)
+    return p, v
+
+
+def macro_to_micro(cap, r_last, u_last, free_space, veh_len, dt):
+    """Conversion.macro_to_micro (road/network/conversion.py:15-73) for J junctions.
+    Returns (cap_out, spawn[int32], v_new, a_new)."""
+    return MacroToMicroFn.apply(cap, r_last, u_last, free_space.detach(), veh_len.detach(), dt)
+
+
+def micro_to_macro(p_head, v_head, a_head, len_head, lane_len, r, y, u, dx, umax):
+    """Conversion.micro_to_macro (road/network/conversion.py:75-171) for J junctions x [J, N] downstream cells.
+    Returns (r_out, y_out, u_out, absorbed[int32], ntouched[int32])."""
+    return MicroToMacroFn.apply(p_head, v_head, a_head, len_head.detach(), lane_len.detach(), r, y, u, dx.detach(),
+                                umax.detach())

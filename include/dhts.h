@@ -1,0 +1,226 @@
+/*
+ * dhts.h -- C ABI of libdhts_b200.so: the B200 (sm_100a) simulation-step kernels
+ * behind the lane / network object API of SonSang/diff-hybrid-traffic-sim.
+ *
+ * The reference has no FFI of its own (it is pure Python); the seam these entry
+ * points replace is its per-lane autograd operator pair
+ *     dMacroForwardLayer  road/lane/dmacro_lane.py:234-310
+ *     dMicroForwardLayer  road/lane/dmicro_lane.py:228-297
+ * plus the T-step loop that chains them (example/inverse/_inverse.py:91-99,227)
+ * and the macro<->micro exchange (road/network/conversion.py:15-215).
+ * INTEGRATION.md shows the ctypes binding a reference maintainer would add.
+ *
+ * Conventions
+ *  - Every pointer is a DEVICE pointer owned by the caller (torch tensors on the
+ *    Python side); the library never allocates, frees or retains them.
+ *  - Every call only ENQUEUES work on `stream` (a cudaStream_t passed as void*)
+ *    of the current device and never synchronises.  Re-entrant; no global or
+ *    thread-local state besides cached device attributes.
+ *  - `_f64` / `_f32`: T = double / float for storage and arithmetic.
+ *  - Return value: DHTS_OK or an error code; nothing is enqueued on error.
+ *  - `flags` is a caller-zeroed int32[4]: flags[0] is a bit mask OR-ed by the
+ *    kernels, flags[1] counts collisions.  The host maps the bits to the
+ *    reference's conventions after the rollout:
+ *      DHTS_FLAG_CFL       AssertionError "Time step size does not meet CFL
+ *                          condition" (road/lane/_macro_lane.py:141-146)
+ *      DHTS_FLAG_NAN_GRAD  AssertionError on NaN gradients (dmacro_lane.py:308)
+ *      DHTS_FLAG_COLLISION print-and-continue (road/lane/_micro_lane.py:151-162)
+ *  - Macro lanes: B lanes x N cells, row-major [B][N]; "padded" arrays are
+ *    [B][N+2] = (left ghost, cells, right ghost) exactly like the operator's
+ *    input vectors (dmacro_lane.py:134-158).  dx[B], umax[B] are per lane.
+ *  - Micro lanes: vehicles lane by lane, index 0 = tail, leader of i is i+1
+ *    (road/lane/_micro_lane.py:33-36); lane_off[L+1] are CSR offsets; params is
+ *    [6][V] = accel_max, accel_pref, target_speed, min_space, time_pref, length
+ *    (road/vehicle/micro_vehicle.py:20-28); head[L][2] = (head_position_delta,
+ *    head_speed_delta) (_micro_lane.py:40-43).
+ */
+#ifndef DHTS_H
+#define DHTS_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DHTS_OK 0
+#define DHTS_ERR_INVALID 1      /* null pointer / negative size / inconsistent arguments */
+#define DHTS_ERR_UNSUPPORTED 2  /* shape outside what the fused kernel handles; use the step entry points */
+#define DHTS_ERR_CUDA 3         /* launch failed (cudaGetLastError) */
+
+#define DHTS_FLAG_CFL 1
+#define DHTS_FLAG_NAN_GRAD 2
+#define DHTS_FLAG_COLLISION 4
+
+int dhts_version(void);
+
+/* ---------------------------------------------------------------- ARZ, one step
+ * Forward half of dMacroForwardLayer (dmacro_lane.py:236-275 -> MacroLane.forward,
+ * _macro_lane.py:83-146; Riemann solver model/macro/_arz.py:212-332).
+ *   r_pad, y_pad, u_pad [B][N+2]  cell records incl. ghosts; u_pad is the speed
+ *                                 STORED on the cell (the reference does not
+ *                                 recompute it at use)
+ *   ueq_pad [B][N+2] or NULL      stored u_eq; NULL = u_eq(r) (only cells
+ *                                 rewritten by micro_to_macro differ)
+ *   nr, ny, nu [B][N]             next density, relative flow and
+ *                                 nu = compute_u(nr, ny) (set_r_y, _arz.py:88-92)
+ *   case_out [B][N+1] or NULL     Riemann outcome per interface (0 Q_L, 1 Q_M, 2 Q_C)
+ */
+int dhts_arz_step_fwd_f64(const double* r_pad, const double* y_pad, const double* u_pad, const double* ueq_pad,
+                          const double* dx, const double* umax, double dt, int B, int N, double* nr, double* ny,
+                          double* nu, int* case_out, int* flags, void* stream);
+int dhts_arz_step_fwd_f32(const float* r_pad, const float* y_pad, const float* u_pad, const float* ueq_pad,
+                          const float* dx, const float* umax, float dt, int B, int N, float* nr, float* ny, float* nu,
+                          int* case_out, int* flags, void* stream);
+
+/* Backward half (dmacro_lane.py:96-132 Jacobian band + :277-310 VJP; Jacobians
+ * model/macro/darz.py:12-233), evaluated from the saved INPUTS of the step.
+ *   g_nr, g_ny [B][N]      adjoint of the outputs;  g_nu [B][N] or NULL adjoint of
+ *                          nu (then nr, ny -- the saved outputs -- are required)
+ *   g_r_pad, g_y_pad [B][N+2]  adjoint of the padded inputs, ghost entries included
+ */
+int dhts_arz_step_bwd_f64(const double* r_pad, const double* y_pad, const double* u_pad, const double* ueq_pad,
+                          const double* dx, const double* umax, double dt, int B, int N, const double* nr,
+                          const double* ny, const double* g_nr, const double* g_ny, const double* g_nu,
+                          double* g_r_pad, double* g_y_pad, int* flags, void* stream);
+int dhts_arz_step_bwd_f32(const float* r_pad, const float* y_pad, const float* u_pad, const float* ueq_pad,
+                          const float* dx, const float* umax, float dt, int B, int N, const float* nr, const float* ny,
+                          const float* g_nr, const float* g_ny, const float* g_nu, float* g_r_pad, float* g_y_pad,
+                          int* flags, void* stream);
+
+/* ---------------------------------------------------------------- ARZ, fused T-step rollout
+ * `steps` x (RoadNetwork.forward over disconnected macro lanes): ghosts are
+ * static per lane (road/network/road_network.py:299-387 with no neighbour),
+ * lane.forward, update_state.  The whole lane stays in shared memory.
+ *   r0, y0 [B][N]; u0 [B][N] or NULL (stored speed of the initial cells, set_r_u)
+ *   ghost [B][2][3]        (r, y, u) of the left / right ghost cell
+ *   ckpt [S][2][B][N] or NULL, S = ceil(steps/ckpt_every): state BEFORE steps
+ *                          0, K, 2K, ... (needed by the backward entry point)
+ *   rT, yT, uT [B][N]      final state, uT = compute_u(rT, yT)
+ * Returns DHTS_ERR_UNSUPPORTED when a lane does not fit in shared memory.
+ */
+int dhts_arz_rollout_fwd_f64(const double* r0, const double* y0, const double* u0, const double* ghost,
+                             const double* dx, const double* umax, double dt, int B, int N, int steps, int ckpt_every,
+                             double* ckpt, double* rT, double* yT, double* uT, int* flags, void* stream);
+int dhts_arz_rollout_fwd_f32(const float* r0, const float* y0, const float* u0, const float* ghost, const float* dx,
+                             const float* umax, float dt, int B, int N, int steps, int ckpt_every, float* ckpt,
+                             float* rT, float* yT, float* uT, int* flags, void* stream);
+
+/* Scratch (in elements of T) the backward rollout needs for (B, N, ckpt_every);
+ * -1 if unsupported.  Depends on the current device's SM count. */
+long long dhts_arz_rollout_scratch_elems_f64(int B, int N, int ckpt_every);
+long long dhts_arz_rollout_scratch_elems_f32(int B, int N, int ckpt_every);
+
+/* Adjoint through time: segments walked backwards, each recomputed from its
+ * checkpoint, then the per-step VJP of dmacro_lane.py:277-310 applied.
+ *   g_rT, g_yT, g_uT [B][N] (each may be NULL = zero); rT, yT needed iff g_uT
+ *   g_r0, g_y0 [B][N]      adjoint of (r0, y0)
+ *   g_ghost [B][2][2] or NULL  adjoint of the ghost (r, y), summed over steps
+ */
+int dhts_arz_rollout_bwd_f64(const double* ckpt, const double* u0, const double* ghost, const double* dx,
+                             const double* umax, double dt, int B, int N, int steps, int ckpt_every, const double* rT,
+                             const double* yT, const double* g_rT, const double* g_yT, const double* g_uT,
+                             double* scratch, long long scratch_elems, double* g_r0, double* g_y0, double* g_ghost,
+                             int* flags, void* stream);
+int dhts_arz_rollout_bwd_f32(const float* ckpt, const float* u0, const float* ghost, const float* dx,
+                             const float* umax, float dt, int B, int N, int steps, int ckpt_every, const float* rT,
+                             const float* yT, const float* g_rT, const float* g_yT, const float* g_uT, float* scratch,
+                             long long scratch_elems, float* g_r0, float* g_y0, float* g_ghost, int* flags,
+                             void* stream);
+
+/* ---------------------------------------------------------------- IDM, one step
+ * Forward half of dMicroForwardLayer (dmicro_lane.py:230-269 -> MicroLane.forward,
+ * _micro_lane.py:131-214; model/micro/_idm.py:5-51).
+ *   veh_lane [V]        lane index of each vehicle (dhts_csr_expand)
+ *   np_, nv_ [V]        next position / speed
+ *   vflags [V] or NULL  bit0 acceleration clipped, bit1 s* clipped, bit2 collision
+ */
+int dhts_csr_expand(const int* lane_off, int L, int* veh_lane, void* stream);
+int dhts_idm_step_fwd_f64(const double* p, const double* v, const double* params, const int* lane_off,
+                          const int* veh_lane, const double* head, double dt, int V, int L, double* np_, double* nv_,
+                          int* vflags, int* flags, void* stream);
+int dhts_idm_step_fwd_f32(const float* p, const float* v, const float* params, const int* lane_off,
+                          const int* veh_lane, const float* head, float dt, int V, int L, float* np_, float* nv_,
+                          int* vflags, int* flags, void* stream);
+
+/* Backward half (dmicro_lane.py:87-127 band, :271-297 VJP; model/micro/didm.py).
+ * The ghost leader of dmicro_lane.py:144-151 (p_head + dp, v_head - dv) is folded
+ * in: its adjoint is added to the head vehicle and returned as g_head[L][2]
+ * (adjoint of head_position_delta, head_speed_delta; may be NULL). */
+int dhts_idm_step_bwd_f64(const double* p, const double* v, const double* params, const int* lane_off,
+                          const int* veh_lane, const double* head, double dt, int V, int L, const double* g_np,
+                          const double* g_nv, double* g_p, double* g_v, double* g_head, int* flags, void* stream);
+int dhts_idm_step_bwd_f32(const float* p, const float* v, const float* params, const int* lane_off,
+                          const int* veh_lane, const float* head, float dt, int V, int L, const float* g_np,
+                          const float* g_nv, float* g_p, float* g_v, float* g_head, int* flags, void* stream);
+
+/* ---------------------------------------------------------------- IDM, fused T-step rollout
+ * One warp per lane, vehicles in registers, leaders by warp shuffle.  max_lane =
+ * largest lane size (<= dhts_idm_rollout_max_lane()); ckpt [S][2][V];
+ * the backward needs ckpt_every <= dhts_idm_rollout_max_ckpt_every(). */
+int dhts_idm_rollout_max_lane(void);
+int dhts_idm_rollout_max_ckpt_every(void);
+int dhts_idm_rollout_fwd_f64(const double* p0, const double* v0, const double* params, const int* lane_off,
+                             const double* head, double dt, int V, int L, int max_lane, int steps, int ckpt_every,
+                             double* ckpt, double* pT, double* vT, int* flags, void* stream);
+int dhts_idm_rollout_fwd_f32(const float* p0, const float* v0, const float* params, const int* lane_off,
+                             const float* head, float dt, int V, int L, int max_lane, int steps, int ckpt_every,
+                             float* ckpt, float* pT, float* vT, int* flags, void* stream);
+int dhts_idm_rollout_bwd_f64(const double* ckpt, const double* params, const int* lane_off, const double* head,
+                             double dt, int V, int L, int max_lane, int steps, int ckpt_every, const double* g_pT,
+                             const double* g_vT, double* g_p0, double* g_v0, double* g_head, int* flags,
+                             void* stream);
+int dhts_idm_rollout_bwd_f32(const float* ckpt, const float* params, const int* lane_off, const float* head, float dt,
+                             int V, int L, int max_lane, int steps, int ckpt_every, const float* g_pT,
+                             const float* g_vT, float* g_p0, float* g_v0, float* g_head, int* flags, void* stream);
+
+/* ---------------------------------------------------------------- macro <-> micro exchange (per junction)
+ * macro -> micro, road/network/conversion.py:15-73 (with MacroLane.add_flux_capacitor,
+ * road/lane/_macro_lane.py:215-225, and MicroLane.entering_free_space,
+ * road/lane/_micro_lane.py:289-301, evaluated by the caller into free_space):
+ *   cap' = cap + r_last u_last dt; spawn iff cap' >= veh_len and free_space >= veh_len;
+ *   on spawn: v_new = u_last, a_new = veh_len carrying d(cap'), cap_out = cap' - veh_len
+ *   with its adjoint cut (the reference re-creates it detached); else cap_out = cap'.
+ * All arrays [J].  spawn is int32. */
+int dhts_m2c_fwd_f64(const double* cap, const double* r_last, const double* u_last, const double* free_space,
+                     const double* veh_len, double dt, int J, double* cap_out, int* spawn, double* v_new,
+                     double* a_new, void* stream);
+int dhts_m2c_fwd_f32(const float* cap, const float* r_last, const float* u_last, const float* free_space,
+                     const float* veh_len, float dt, int J, float* cap_out, int* spawn, float* v_new, float* a_new,
+                     void* stream);
+int dhts_m2c_bwd_f64(const double* r_last, const double* u_last, const int* spawn, double dt, int J,
+                     const double* g_cap_out, const double* g_v_new, const double* g_a_new, double* g_cap,
+                     double* g_r_last, double* g_u_last, void* stream);
+int dhts_m2c_bwd_f32(const float* r_last, const float* u_last, const int* spawn, float dt, int J,
+                     const float* g_cap_out, const float* g_v_new, const float* g_a_new, float* g_cap,
+                     float* g_r_last, float* g_u_last, void* stream);
+
+/* micro -> macro, road/network/conversion.py:75-171: when the head vehicle has
+ * passed lane_len + len it is absorbed: every downstream cell it overlaps (walking
+ * from cell 0 until the first miss) gets r += (a/len)(overlap/dx) value-clamped to
+ * [1e-5, 1-1e-5] with pass-through gradient, u = v_head, y = r (u - u_eq(r)).
+ *   p_head, v_head, a_head, len_head, lane_len, dx, umax [J]; r, y, u [J][N] rows of
+ *   the downstream macro lanes; outputs are full rows; absorbed, ntouched int32 [J].
+ * The backward takes the saved r_out / ntouched and returns the adjoints of
+ * (p_head, v_head, a_head) and of the input rows. */
+int dhts_c2m_fwd_f64(const double* p_head, const double* v_head, const double* a_head, const double* len_head,
+                     const double* lane_len, const double* r, const double* y, const double* u, const double* dx,
+                     const double* umax, int J, int N, double* r_out, double* y_out, double* u_out, int* absorbed,
+                     int* ntouched, void* stream);
+int dhts_c2m_fwd_f32(const float* p_head, const float* v_head, const float* a_head, const float* len_head,
+                     const float* lane_len, const float* r, const float* y, const float* u, const float* dx,
+                     const float* umax, int J, int N, float* r_out, float* y_out, float* u_out, int* absorbed,
+                     int* ntouched, void* stream);
+int dhts_c2m_bwd_f64(const double* p_head, const double* v_head, const double* a_head, const double* len_head,
+                     const double* lane_len, const double* r_out, const double* dx, const double* umax,
+                     const int* ntouched, int J, int N, const double* g_r_out, const double* g_y_out,
+                     const double* g_u_out, double* g_p, double* g_v, double* g_a, double* g_r, double* g_y,
+                     double* g_u, void* stream);
+int dhts_c2m_bwd_f32(const float* p_head, const float* v_head, const float* a_head, const float* len_head,
+                     const float* lane_len, const float* r_out, const float* dx, const float* umax,
+                     const int* ntouched, int J, int N, const float* g_r_out, const float* g_y_out,
+                     const float* g_u_out, float* g_p, float* g_v, float* g_a, float* g_r, float* g_y, float* g_u,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DHTS_H */

@@ -1,0 +1,90 @@
+"""Pins the CPU oracle (oracle/dhts_oracle.c) against outputs of the LIVE reference frozen in
+tests/golden/ by oracle/gen_golden.py: dtype-proxied fp64 reference (tier 2) to rounding, and the
+reference as shipped (fp32 storage, tier 1) to fp32 rounding."""
+import numpy as np
+import pytest
+
+from conftest import golden, relerr
+from oracle import oracle as O
+
+TIERS = [("fp64", False, 1e-12, 1e-11), ("fp32", True, 2e-5, 2e-4)]
+
+
+@pytest.mark.parametrize("tier,f32,tol_s,tol_g", TIERS)
+def test_arz_step(tier, f32, tol_s, tol_g):
+    g = golden("arz_step_" + tier)
+    hist = np.zeros(3, dtype=int)
+    for k in range(g["pr"].shape[0]):
+        o = O.arz_step(g["pr"][k], g["py"][k], g["pu"][k], g["pe"][k], float(g["dx"]), float(g["umax"]), float(g["dt"]),
+                       f32=f32)
+        assert (o["case"] == g["case"][k]).all()
+        hist += np.bincount(o["case"], minlength=3)
+        assert np.abs(o["speeds"] - g["speeds"][k]).max() < (1e-9 if not f32 else 1e-3)
+        assert relerr(o["nr"], g["nr"][k]) < tol_s and relerr(o["ny"], g["ny"][k]) < tol_s
+        assert relerr(o["nu"], g["nu"][k]) < max(tol_s, 1e-12) * 10
+        assert relerr(o["dqs"], g["dqs"][k]) < tol_g
+        gr, gy = O.arz_vjp(o["dqs"], g["g_nr"][k], g["g_ny"][k], f32=f32)
+        assert relerr(gr, g["g_r"][k]) < tol_g and relerr(gy, g["g_y"][k]) < tol_g
+        assert o["cfl"] == 0
+    assert (hist > 50).all(), hist      # all three Riemann outcomes are exercised
+
+
+@pytest.mark.parametrize("tier,f32,tol_s,tol_g", TIERS)
+def test_arz_rollout(tier, f32, tol_s, tol_g):
+    g = golden("arz_rollout_" + tier)
+    T = int(g["T"])
+    o = O.arz_rollout(g["r0"], g["u0"], g["ghost_ru"], float(g["dx"]), float(g["umax"]), float(g["dt"]), T, f32=f32,
+                      g_rT=g["w_r"], g_uT=g["w_u"], want_hist=True)
+    assert o["cfl"] == 0
+    for a, b in (("rT", "rT"), ("yT", "yT"), ("uT", "uT")):
+        assert relerr(o[a], g[b]) < tol_s * 10, a
+    for i, t in enumerate(g["snaps"]):
+        assert relerr(o["hist"][int(t)], g["snap"][:, i]) < tol_s * 10
+    for a in ("g_r0", "g_u0", "g_ghost"):
+        assert relerr(o[a], g[a]) < tol_g, a
+
+
+@pytest.mark.parametrize("tier,f32,tol_s,tol_g", TIERS)
+def test_idm_step(tier, f32, tol_s, tol_g):
+    g = golden("idm_step_" + tier)
+    seen = 0
+    for k in range(g["p"].shape[0]):
+        o = O.idm_step(g["p"][k], g["v"][k], g["params"][k], g["head"][k][0], g["head"][k][1], float(g["dt"]), f32=f32)
+        assert ((o["flags"] & 3) == g["flags"][k]).all()
+        seen |= int(np.bitwise_or.reduce(o["flags"]))
+        assert relerr(o["np"], g["np"][k]) < tol_s and relerr(o["nv"], g["nv"][k]) < tol_s
+        assert relerr(o["dqs"], g["dqs"][k]) < tol_g
+        gp, gs = O.idm_vjp(o["dqs"], g["g_np"][k], g["g_ns"][k], f32=f32)
+        assert relerr(gp, g["g_p"][k]) < tol_g and relerr(gs, g["g_s"][k]) < tol_g
+    assert seen & 1 and seen & 2        # both clips are exercised
+
+
+@pytest.mark.parametrize("tier,f32,tol_s,tol_g", TIERS)
+def test_idm_rollout(tier, f32, tol_s, tol_g):
+    g = golden("idm_rollout_" + tier)
+    T, L, n = int(g["T"]), int(g["L"]), int(g["n"])
+    params = np.concatenate([g["params"][l] for l in range(L)], axis=1)
+    off = np.arange(L + 1) * n
+    o = O.idm_rollout(g["p0"].ravel(), g["v0"].ravel(), params, off, g["head"], float(g["dt"]), T, f32=f32,
+                      g_pT=g["w_p"].ravel(), g_vT=g["w_v"].ravel(), want_hist=True)
+    assert o["ncol"] == 0
+    assert relerr(o["pT"], g["pT"].ravel()) < tol_s and relerr(o["vT"], g["vT"].ravel()) < tol_s
+    for i, t in enumerate(g["snaps"]):
+        assert relerr(o["hist"][int(t)].reshape(L, n, 2), g["snap"][:, i]) < tol_s
+    assert relerr(o["g_p0"], g["g_p0"].ravel()) < tol_g and relerr(o["g_v0"], g["g_v0"].ravel()) < tol_g
+    assert relerr(o["g_head"], g["g_head"]) < tol_g
+
+
+def test_oracle_edge_cases():
+    # one-cell lane, vacuum everywhere, collision flagging, empty lanes
+    o = O.arz_step([0.3, 0.5, 0.2], [0.0, 0.1, 0.0], [10.0, 12.0, 9.0], [20.0, 18.0, 22.0], 5.0, 30.0, 0.01)
+    assert o["nr"].shape == (1,) and np.isfinite(o["nr"]).all()
+    o = O.arz_step(np.zeros(6), np.zeros(6), np.full(6, 30.0), np.full(6, 30.0), 5.0, 30.0, 0.01)
+    assert (o["case"] == 0).all() and np.abs(o["nr"]).max() == 0
+    assert O.arz_step([0.5, 0.5, 0.5], [0, 0, 0], [29.0, 29.0, 29.0], [9.0, 9.0, 9.0], 0.1, 30.0, 0.01)["cfl"] == 1
+    par = np.array([[30.0] * 2, [24.0] * 2, [27.0] * 2, [0.5] * 2, [0.1] * 2, [5.0] * 2])
+    o = O.idm_step([0.0, 3.0], [10.0, 10.0], par, 1000.0, 0.0, 0.01)
+    assert o["ncol"] == 1 and o["flags"][0] & 4
+    o = O.idm_rollout(np.zeros(0), np.zeros(0), np.zeros((6, 0)), [0, 0, 0], np.zeros((2, 2)), 0.01, 3,
+                      g_pT=np.zeros(0), g_vT=np.zeros(0))
+    assert o["pT"].shape == (0,)
