@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""Headline benchmark: fwd+bwd cell-updates/s (ARZ) and vehicle-updates/s (IDM) on the synthetic batch of
+BASELINE.json configs[4]: per GPU 65536 independent ARZ lanes x 1024 cells + 4,194,304 IDM vehicles
+(65536 lanes x 64), 1000 simulation steps forward + adjoint.
+
+One bench "step" = one full pass of the hot path over that batch: ARZ rollout fwd + loss + adjoint, IDM
+rollout fwd + loss + adjoint (one update = one cell / vehicle advanced one simulation step forward AND its
+adjoint propagated one step back).  Lanes are independent, so ranks hold independent shards
+(weak scaling) and the only collective is one all-reduce of the scalar losses per pass.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]             # our CUDA path
+    python bench.py --impl reference ...                            # CPU arm (oracle port, all host threads)
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for how each field is derived.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# algorithmic bytes per update, single-pass streaming model, in scalars of the state dtype
+ARZ_SCALARS_FWD, ARZ_SCALARS_BWD = 4, 6          # fwd: read (r,y) write (r,y); bwd: read (r,y), read adj, write adj
+IDM_SCALARS_FWD, IDM_SCALARS_BWD = 10, 12        # fwd: read (p,v)+6 params, write (p,v); bwd: read 8 + adj 2 + write 2
+SEED = 20221008
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--lanes", type=int, default=65536, help="ARZ lanes per GPU")
+    ap.add_argument("--cells", type=int, default=1024)
+    ap.add_argument("--micro-lanes", type=int, default=65536, help="IDM lanes per GPU")
+    ap.add_argument("--lane-vehicles", type=int, default=64)
+    ap.add_argument("--sim-steps", type=int, default=1000)
+    ap.add_argument("--ckpt-every", type=int, default=32)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return ("synthetic batch per GPU: %d ARZ lanes x %d cells + %d IDM vehicles (%d lanes x %d), %d steps fwd+bwd"
+            % (a.lanes, a.cells, a.micro_lanes * a.lane_vehicles, a.micro_lanes, a.lane_vehicles, a.sim_steps))
+
+
+# ----------------------------------------------------------------------------------------- synthetic inputs
+
+def make_arz_inputs(a, shard, torch):
+    """SURVEY 8(d) 'Synthetic ARZ input' (C1's physics, example/inverse/macro.py:48-49,88-89,246-252)."""
+    g = torch.Generator().manual_seed(SEED + shard)
+    B, N, umax = a.lanes, a.cells, 30.0
+    r0 = torch.rand((B, N), generator=g, dtype=torch.float32)
+    u0 = torch.rand((B, N), generator=g, dtype=torch.float32) * umax
+    gr = torch.rand((B, 2), generator=g, dtype=torch.float32)
+    gu = torch.rand((B, 2), generator=g, dtype=torch.float32) * umax
+    tr = torch.rand((B, N), generator=g, dtype=torch.float32)
+    tu = torch.rand((B, N), generator=g, dtype=torch.float32) * umax
+    return dict(r0=r0, u0=u0, gr=gr, gu=gu, tr=tr, tu=tu, dx=5.0, umax=umax, dt=0.01)
+
+
+def make_idm_inputs(a, shard, torch):
+    """SURVEY 8(d) 'Synthetic IDM input' (example/inverse/micro.py:77-81; road/vehicle/micro_vehicle.py:88-109)."""
+    g = torch.Generator().manual_seed(SEED + 7919 + shard)
+    L, n, umax = a.micro_lanes, a.lane_vehicles, 30.0
+    V = L * n
+    rnd = lambda *s: torch.rand(s, generator=g, dtype=torch.float32)
+    p0 = (torch.arange(n, dtype=torch.float32)[None, :] * 20.0 + rnd(L, n) * 10.0).reshape(V)
+    v0 = 9.0 + 12.0 * rnd(V)
+    params = torch.stack([(1.5 + 0.5 * rnd(V)) * umax, (1.0 + 0.5 * rnd(V)) * umax, (0.8 + 0.4 * rnd(V)) * umax,
+                          1.0 + rnd(V), 0.2 + 0.4 * rnd(V), torch.full((V,), 5.0)])
+    tp = p0 + 0.01 * 1000 * 15.0 + rnd(V)
+    tv = 9.0 + 12.0 * rnd(V)
+    off = (torch.arange(L + 1, dtype=torch.int64) * n).to(torch.int32)
+    head = torch.tensor([[1000.0, 0.0]], dtype=torch.float32).repeat(L, 1)
+    return dict(p0=p0, v0=v0, params=params, tp=tp, tv=tv, off=off, head=head, dt=0.01, n=n)
+
+
+# ----------------------------------------------------------------------------------------- clocks sampler
+
+class Clocks:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ts, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8 or not (t0 <= ts <= t1 + 0.3):
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------- CPU arms
+
+def cpu_port_rates(a, seconds_budget=12.0):
+    """Times the oracle port (oracle/dhts_oracle.c, OpenMP over lanes) on a bounded sample of the workload:
+    lanes of the config's shape (N cells / n vehicles), fewer lanes and fewer steps.  Returns rates + sample text."""
+    import numpy as np
+    from oracle import oracle as O
+    cores = len(os.sched_getaffinity(0))
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    rng = np.random.default_rng(SEED)
+    N, n, umax = a.cells, a.lane_vehicles, 30.0
+
+    def arz(B, T):
+        r0 = rng.uniform(0, 1, (B, N)); u0 = rng.uniform(0, 1, (B, N)) * umax
+        gh = np.stack([rng.uniform(0, 1, (B, 2)), rng.uniform(0, 1, (B, 2)) * umax], -1)
+        w = rng.normal(size=(B, N))
+        t = time.perf_counter()
+        O.arz_rollout(r0, u0, gh, 5.0, umax, 0.01, T, g_rT=w, g_uT=w / umax)
+        return B * N * T / (time.perf_counter() - t)
+
+    def idm(L, T):
+        V = L * n
+        p0 = (np.arange(n)[None] * 20.0 + rng.uniform(0, 10, (L, n))).ravel(); v0 = rng.uniform(9, 21, V)
+        par = np.stack([rng.uniform(1.5, 2, V) * umax, rng.uniform(1, 1.5, V) * umax, rng.uniform(0.8, 1.2, V) * umax,
+                        rng.uniform(1, 2, V), rng.uniform(0.2, 0.6, V), np.full(V, 5.0)])
+        off = np.arange(L + 1) * n; head = np.tile([[1000.0, 0.0]], (L, 1)); w = rng.normal(size=V)
+        t = time.perf_counter()
+        O.idm_rollout(p0, v0, par, off, head, 0.01, T, g_pT=w, g_vT=w)
+        return V * T / (time.perf_counter() - t)
+
+    Ta, Ti = min(20, a.sim_steps), min(100, a.sim_steps)
+    probe_a = arz(cores, Ta)                      # calibrate, then size the timed sample to the budget
+    Ba = int(max(cores, min(a.lanes, probe_a * seconds_budget * 0.5 / (N * Ta))))
+    rate_a = arz(Ba, Ta)
+    probe_i = idm(cores * 4, Ti)
+    Li = int(max(cores, min(a.micro_lanes, probe_i * seconds_budget * 0.5 / (n * Ti))))
+    rate_i = idm(Li, Ti)
+    sample = ("%d ARZ lanes x %d cells x %d steps fwd+bwd; %d IDM lanes x %d vehicles x %d steps fwd+bwd; "
+              "OpenMP over lanes" % (Ba, N, Ta, Li, n, Ti))
+    return rate_a, rate_i, cores, sample
+
+
+def run_reference(a):
+    """CPU arm.  The reference is pure Python (no C sources to compile into oracle/_ref) and cannot travel to the
+    GPU box, so this times the oracle port with every host thread, on a bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t0 = time.time()
+    budget = max(4.0, min(20.0, 150.0 / max(1, a.steps + a.warmup)))
+    for _ in range(a.warmup):
+        cpu_port_rates(a, budget)
+    ra, ri, ms = [], [], []
+    for _ in range(max(1, a.steps)):
+        t = time.perf_counter()
+        x, y, cores, sample = cpu_port_rates(a, budget)
+        ms.append((time.perf_counter() - t) * 1e3); ra.append(x); ri.append(y)
+    va, vi = sum(ra) / len(ra), sum(ri) / len(ri)
+    line = {"impl": "reference", "metric": "fwd+bwd cell-updates/s", "value": va, "unit": "cell-updates/s",
+            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": sum(ms) / len(ms),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(a), "sample_per_step": sample},
+            "idm": {"value": vi, "unit": "vehicle-updates/s"},
+            "cpu_baseline": {"value": va, "unit": "cell-updates/s", "cores": cores, "kind": "port", "sample": sample,
+                             "idm_value": vi, "idm_unit": "vehicle-updates/s",
+                             "note": "C port of the reference step (oracle/); the reference's own Python path measured "
+                                     "4.3e3 cell-updates/s and 9.3e3 vehicle-updates/s per core (BASELINE.md sec. 2)"},
+            "e2e": {"value": va, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": time.time() - t0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------- our arm
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    import dhts_b200
+    from dhts_b200 import functional as F
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback of the product path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    dhts_b200._lib.load()
+    dt_t = torch.float64 if a.dtype == "f64" else torch.float32
+    esz = 8 if a.dtype == "f64" else 4
+
+    A = make_arz_inputs(a, rank, torch)
+    M = make_idm_inputs(a, rank, torch)
+    pin = lambda t: t.to(dt_t if t.is_floating_point() else t.dtype).pin_memory()
+    hostA = {k: pin(v) for k, v in A.items() if hasattr(v, "shape")}
+    hostM = {k: pin(v) for k, v in M.items() if hasattr(v, "shape")}
+    devA = {k: v.to(dev) for k, v in hostA.items()}
+    devM = {k: v.to(dev) for k, v in hostM.items()}
+    flags = dhts_b200.Flags(dev)
+    B, N, T = a.lanes, a.cells, a.sim_steps
+    V = a.micro_lanes * a.lane_vehicles
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def arz_pass(d, timers=None):
+        r0 = d["r0"].detach().requires_grad_(); u0 = d["u0"].detach().requires_grad_()
+        if timers: timers[0].record()
+        rT, yT, uT = F.arz_rollout(r0, u0, d["gr"], d["gu"], A["dx"], A["umax"], A["dt"], T, ckpt_every=a.ckpt_every,
+                                   flags=flags)
+        if timers: timers[1].record()
+        loss = ((rT - d["tr"]) ** 2).sum() + ((uT - d["tu"]) ** 2).sum()     # example/inverse/macro.py:226-241
+        if timers: timers[2].record()
+        loss.backward()
+        if timers: timers[3].record()
+        return loss.detach(), r0.grad, u0.grad
+
+    def idm_pass(d, timers=None):
+        p0 = d["p0"].detach().requires_grad_(); v0 = d["v0"].detach().requires_grad_()
+        if timers: timers[0].record()
+        pT, vT = F.idm_rollout(p0, v0, d["params"], d["off"], d["head"], M["dt"], T, ckpt_every=a.ckpt_every,
+                               flags=flags, max_lane=M["n"])
+        if timers: timers[1].record()
+        loss = ((pT - d["tp"]) ** 2).sum() + ((vT - d["tv"]) ** 2).sum()     # example/inverse/micro.py:221-236
+        if timers: timers[2].record()
+        loss.backward()
+        if timers: timers[3].record()
+        return loss.detach(), p0.grad, v0.grad
+
+    def reduce_loss(la, li):
+        t = torch.stack([la, li])
+        if world > 1:
+            dist.all_reduce(t)          # the only collective: scalar losses over the lane shards
+        return t
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident pass (value): inputs already in HBM
+    for _ in range(a.warmup):
+        la, _, _ = arz_pass(devA); li, _, _ = idm_pass(devM); reduce_loss(la, li)
+    barrier()
+    clocks = Clocks(local) if rank == 0 else None
+    t_wall0 = time.time()
+    tA = [[ev() for _ in range(4)] for _ in range(a.steps)]
+    tM = [[ev() for _ in range(4)] for _ in range(a.steps)]
+    e0, e1 = ev(), ev()
+    e0.record()
+    for s in range(a.steps):
+        la, _, _ = arz_pass(devA, tA[s]); li, _, _ = idm_pass(devM, tM[s]); losses = reduce_loss(la, li)
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    clk = clocks.stop(t_wall0, t_wall1) if clocks else None
+    total_ms = e0.elapsed_time(e1)
+    arz_fwd = sum(t[0].elapsed_time(t[1]) for t in tA); arz_bwd = sum(t[2].elapsed_time(t[3]) for t in tA)
+    arz_all = sum(t[0].elapsed_time(t[3]) for t in tA)
+    idm_fwd = sum(t[0].elapsed_time(t[1]) for t in tM); idm_bwd = sum(t[2].elapsed_time(t[3]) for t in tM)
+    idm_all = sum(t[0].elapsed_time(t[3]) for t in tM)
+    bits, ncol = flags.read()
+
+    # ---- end-to-end pass: host (pinned) inputs -> H2D -> rollouts -> D2H of losses and gradients, every step
+    e2e_ms = None
+    h2d = d2h = 0
+    if not a.no_e2e:
+        outA = [torch.empty((B, N), dtype=dt_t).pin_memory() for _ in range(2)]
+        outM = [torch.empty((V,), dtype=dt_t).pin_memory() for _ in range(2)]
+        h2d = sum(v.numel() * v.element_size() for v in hostA.values()) + sum(v.numel() * v.element_size() for v in hostM.values())
+        d2h = sum(t.numel() * t.element_size() for t in outA + outM) + 2 * esz
+
+        def e2e_pass():
+            dA = {k: v.to(dev, non_blocking=True) for k, v in hostA.items()}
+            la, gr0, gu0 = arz_pass(dA)
+            outA[0].copy_(gr0, non_blocking=True); outA[1].copy_(gu0, non_blocking=True)
+            dM = {k: v.to(dev, non_blocking=True) for k, v in hostM.items()}
+            li, gp0, gv0 = idm_pass(dM)
+            outM[0].copy_(gp0, non_blocking=True); outM[1].copy_(gv0, non_blocking=True)
+            return reduce_loss(la, li).cpu()
+
+        e2e_pass()
+        barrier()
+        f0, f1 = ev(), ev()
+        f0.record()
+        for _ in range(a.steps):
+            e2e_pass()
+        f1.record()
+        barrier()
+        e2e_ms = f0.elapsed_time(f1)
+
+    # ---- max over ranks
+    times = torch.tensor([total_ms, arz_all, idm_all, arz_fwd, arz_bwd, idm_fwd, idm_bwd, e2e_ms or 0.0],
+                         dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    total_ms, arz_all, idm_all, arz_fwd, arz_bwd, idm_fwd, idm_bwd, e2e_ms_max = times.tolist()
+
+    if rank == 0:
+        K = a.steps
+        cell_updates = world * B * N * T * K
+        veh_updates = world * V * T * K
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6650 GB/s (of fallback)"
+        # dominant kernel: arz_rollout_bwd (one launch per pass per GPU)
+        bwd_bytes = B * N * T * ARZ_SCALARS_BWD * esz
+        bwd_s = arz_bwd / K / 1e3
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("arz_rollout_bwd_" + a.dtype)
+        except Exception:
+            pass
+        both_bytes = B * N * T * (ARZ_SCALARS_FWD + ARZ_SCALARS_BWD) * esz
+        both_s = (arz_fwd + arz_bwd) / K / 1e3
+        idm_bytes = V * T * (IDM_SCALARS_FWD + IDM_SCALARS_BWD) * esz
+        idm_s = (idm_fwd + idm_bwd) / K / 1e3
+        line = {
+            "metric": "fwd+bwd cell-updates/s", "value": cell_updates / (arz_all / 1e3), "unit": "cell-updates/s",
+            "n_gpus": world, "steps": K, "warmup": a.warmup, "ms_per_step": total_ms / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
+            "config": {"workload": workload_name(a), "arz": {"lanes_per_gpu": B, "cells": N, "dx": 5.0, "dt": 0.01,
+                                                             "u_max": 30.0},
+                       "idm": {"vehicles_per_gpu": V, "lane_vehicles": a.lane_vehicles, "params": "per-vehicle"},
+                       "sim_steps": T, "ckpt_every": a.ckpt_every, "parallelism": "lane shards x%d, all-reduce(loss)" % world,
+                       "l2": "inputs (%.1f GB per pass) are larger than the 126 MB L2" % ((2 * B * N + 8 * V) * esz / 1e9)},
+            "idm": {"metric": "fwd+bwd vehicle-updates/s", "value": veh_updates / (idm_all / 1e3),
+                    "unit": "vehicle-updates/s", "ms_per_step": idm_all / K},
+            "phase_ms_per_step": {"arz_fwd": arz_fwd / K, "arz_bwd": arz_bwd / K, "arz_total": arz_all / K,
+                                  "idm_fwd": idm_fwd / K, "idm_bwd": idm_bwd / K, "idm_total": idm_all / K},
+            "gpu_launches": 4 * K,
+            "roofline": {"kernel": "arz_rollout_bwd_kernel<%s>" % ("double" if a.dtype == "f64" else "float"),
+                         "bound": "hbm", "achieved": bwd_bytes / bwd_s / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": bwd_bytes / bwd_s / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": bwd_bytes,
+                         "note": "achieved = 6 scalars x cell-steps per launch / CUDA-event time of the backward "
+                                 "rollout; temporal fusion keeps real DRAM traffic far below this (see traffic)"},
+            "roofline_fwd_bwd": {"arz": {"achieved": both_bytes / both_s / 1e9, "frac": both_bytes / both_s / 1e9 / peak,
+                                         "bytes_per_update": (ARZ_SCALARS_FWD + ARZ_SCALARS_BWD) * esz},
+                                 "idm": {"achieved": idm_bytes / idm_s / 1e9, "frac": idm_bytes / idm_s / 1e9 / peak,
+                                         "bytes_per_update": (IDM_SCALARS_FWD + IDM_SCALARS_BWD) * esz},
+                                 "unit": "GB/s", "peak": peak},
+            "clocks": clk,
+            "flags": {"bits": bits, "collisions": ncol},
+            "losses": [float(x) for x in losses.tolist()],
+        }
+        if e2e_ms is not None:
+            line["e2e"] = {"value": cell_updates / (e2e_ms_max / 1e3), "unit": "cell-updates/s",
+                           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_max / K,
+                           "note": "whole pass (ARZ + IDM) from pinned host buffers, gradients and losses read back; "
+                                   "value counts ARZ cell-updates over the WHOLE pass time (IDM and copies included)"}
+        if not a.no_cpu_baseline:
+            ra, ri, cores, sample = cpu_port_rates(a)
+            line["cpu_baseline"] = {"value": ra, "unit": "cell-updates/s", "cores": cores, "kind": "port",
+                                    "sample": sample, "idm_value": ri, "idm_unit": "vehicle-updates/s"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
