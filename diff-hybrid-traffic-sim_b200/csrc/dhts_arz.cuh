@@ -28,6 +28,37 @@ template <typename T> __device__ __forceinline__ T t_sqrt(T x);
 template <> __device__ __forceinline__ double t_sqrt<double>(double x) { return sqrt(x); }
 template <> __device__ __forceinline__ float t_sqrt<float>(float x) { return sqrtf(x); }
 template <typename T> __device__ __forceinline__ T t_abs(T x) { return x < T(0) ? -x : x; }
+
+// Branch-free 1/sqrt(x) and 1/x for well-scaled positive x (densities, gaps): hardware
+// approximation (MUFU.RSQ64H / MUFU.RCP64H, ~2^-22) refined to ~1 ulp.  The library
+// sqrt()/division carry special-case slow paths and long dependent Newton chains that
+// dominated the stall profile (profiles/r1a, r1b); parity has >6 digits of headroom.
+template <typename T> __device__ __forceinline__ T f_rsqrt(T x);
+template <> __device__ __forceinline__ double f_rsqrt<double>(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-(x * y), y, 1.0);                 // 1 - x y^2
+    y = fma(y, e * fma(0.375, e, 0.5), y);            // Halley: error^3
+    e = fma(-(x * y), y, 1.0);
+    return fma(y * 0.5, e, y);                        // Newton polish
+}
+template <> __device__ __forceinline__ float f_rsqrt<float>(float x) { return rsqrtf(x); }
+template <typename T> __device__ __forceinline__ T f_rcp(T x);
+template <> __device__ __forceinline__ double f_rcp<double>(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, fma(e, e, e), y);                      // y (1 + e + e^2)
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+template <> __device__ __forceinline__ float f_rcp<float>(float x) { return __frcp_rn(x); }
+// sqrt(x) = x * rsqrt(x) with one correction step (x > 0)
+template <typename T> __device__ __forceinline__ T f_sqrt_pos(T x) {
+    T y = f_rsqrt(x);
+    T s = x * y;
+    return fma(fma(-s, s, x), y * T(0.5), s);
+}
 template <typename T> __device__ __forceinline__ T t_max(T a, T b) { return a > b ? a : b; }
 template <typename T> __device__ __forceinline__ bool t_isnan(T x) { return !(x == x); }
 
@@ -60,18 +91,16 @@ template <typename T> __device__ __forceinline__ T compute_u(T r, T y, T umax) {
 template <typename T, bool ADJ> __device__ __forceinline__ Cell<T> derive_cell(T r, T y, T umax) {
     Cell<T> c;
     T rc = t_max(r, DHTS_EPS);
-    T ueq_c = umax * (T(1) - t_sqrt(rc + DHTS_EPS));   // compute_u evaluates u_eq at the clamped r
+    T re = rc + DHTS_EPS;
+    T ueq_c = umax * (T(1) - f_sqrt_pos(re));          // compute_u evaluates u_eq at the clamped r
     c.r = r; c.y = y;
-    c.sq = t_sqrt(rc);
-    if (ADJ) {
-        c.ri = T(1) / rc; c.rs = c.sq * c.ri;          // 1/sqrt(rc) = sqrt(rc)/rc
-        c.uc = y * c.ri + ueq_c;
-    } else {
-        c.ri = T(0); c.rs = T(0);
-        c.uc = y / rc + ueq_c;
-    }
+    c.rs = f_rsqrt(rc);                                // rc^(gamma-1)
+    c.sq = rc * c.rs;                                  // rc^gamma
+    c.ri = c.rs * c.rs;                                // 1/rc
+    c.uc = y * c.ri + ueq_c;
     c.us = c.uc;
-    c.uf = (r >= DHTS_EPS) ? ueq_c : u_eq(r, umax);    // same value when r >= eps
+    // u_eq(r) differs from ueq_c only below eps (max(r,0)+eps vs max(r,eps)+eps)
+    c.uf = (r >= DHTS_EPS) ? ueq_c : umax * (T(1) - f_sqrt_pos(t_max(r, T(0)) + DHTS_EPS));
     c.w = umax + c.us - c.uf;
     return c;
 }
@@ -94,62 +123,56 @@ template <typename T> struct Riem {
     bool cfl_bad;
 };
 
-// Riemann solve at one interface.  Case tree of _arz.py:225-322, selected state
-// per :324-336.  Where the reference only consumes the SIGN of a wave speed the
-// division is skipped; the CFL test dt < dx / max(|s|,1e-5) is evaluated as
-// dt * max(|s|,1e-5) < dx.
+// Riemann solve at one interface.  Case tree of _arz.py:225-322, selected state per
+// :324-336, written BRANCH-FREE: with a 86/9/5 % outcome mix nearly every warp holds
+// all three outcomes, so a divergent tree executes every path anyway while blocking
+// instruction-level overlap between the C independent cells of a thread.  Where the
+// reference only consumes the SIGN of a wave speed the division is skipped; the CFL
+// test dt < dx / max(|s|,1e-5) is evaluated as dt * max(|s|,1e-5) < dx.
 template <typename T>
 __device__ __forceinline__ Riem<T> riemann(const Cell<T>& L, const Cell<T>& R, T umax, T inv_umax, T inv15, T dt,
                                            T dx) {
     Riem<T> o;
-    T s0 = T(0), s1;
-    bool shock = false; T fd = T(0), den = T(1), b = T(0);
-    if (L.r < DHTS_EPS) {                                          // :225
-        o.cas = 0; s1 = L.us;
-    } else {
-        T lam0l = L.us - T(0.5) * umax * L.sq;                     // u + r u_eq'(r), r >= eps   :103
-        if (R.r < DHTS_EPS) {                                      // :235
-            s0 = (lam0l + L.w) * T(0.5); s1 = s0;
-            o.cas = (lam0l >= T(0)) ? 0 : 2;
-        } else if (t_abs(L.us - R.us) < DHTS_EPS) {                // :256
-            o.cas = 0; s1 = R.us;
-        } else if (L.us > R.us) {                                  // :265 shock
-            b = L.sq + (L.us - R.us) * inv_umax;
-            T rm = b * b;
-            fd = rm * R.us - L.r * L.us;
-            den = t_max(rm - L.r, DHTS_EPS);
-            shock = true; s1 = R.us;
-            o.cas = (fd >= T(0)) ? 0 : 1;
-        } else if (L.w > R.us) {                                   // :283 rarefaction
-            b = L.sq + (L.us - R.us) * inv_umax;
-            T rm = b * b;
-            T lam0m = R.us - T(0.5) * umax * ((rm >= DHTS_EPS) ? t_abs(b) : rm * DHTS_RSQRT_EPS);
-            s0 = (lam0l + lam0m) * T(0.5); s1 = R.us;
-            o.cas = (lam0l >= T(0)) ? 0 : ((lam0m <= T(0)) ? 1 : 2);
-        } else {                                                   // :306 vacuum forms
-            s0 = (lam0l + L.w) * T(0.5); s1 = R.us;
-            o.cas = (lam0l >= T(0)) ? 0 : 2;
-        }
-    }
-    // CFL (_macro_lane.py:137-146)
-    bool ok1 = dt * t_max(t_abs(s1), T(1e-5)) < dx;
-    bool ok0 = shock ? (dt * t_max(t_abs(fd), T(1e-5) * den) < dx * den) : (dt * t_max(t_abs(s0), T(1e-5)) < dx);
-    o.cfl_bad = !(ok0 && ok1);
-    if (o.cas == 0) {                                              // compute_Ql :155-165
-        o.r0 = L.r; o.y0 = L.y; o.u0 = L.uc; o.ueq0 = L.uf; o.rootr = L.sq;
-    } else if (o.cas == 1) {                                       // compute_Qm :186-199
-        o.r0 = b * b; o.u0 = R.us;
-        o.ueq0 = umax * (T(1) - t_sqrt(o.r0 + DHTS_EPS));
-        o.y0 = o.r0 * (o.u0 - o.ueq0);
-        o.rootr = t_abs(b);
-    } else {                                                       // compute_Qc :168-183
-        T sc = L.us + umax * L.sq;
-        T q = sc * inv15;
-        o.r0 = q * q; o.u0 = (T(0.5) / T(1.5)) * sc;
-        o.ueq0 = umax * (T(1) - t_sqrt(o.r0 + DHTS_EPS));
-        o.y0 = o.r0 * (o.u0 - o.ueq0);
-        o.rootr = t_abs(q);
-    }
+    const bool vacL = L.r < DHTS_EPS;                              // :225
+    const bool vacR = R.r < DHTS_EPS;                              // :235
+    const T du = L.us - R.us;
+    const bool same = t_abs(du) < DHTS_EPS;                        // :256
+    const bool shock = du > T(0);                                  // :265
+    const bool rare = L.w > R.us;                                  // :283
+    const T lam0l = L.us - T(0.5) * umax * L.sq;                   // u + r u_eq'(r) for r >= eps   :103
+    const T b = L.sq + du * inv_umax;                              // Q_M: r_m = b^2               :194
+    const T rm = b * b;
+    const T fd = rm * R.us - L.r * L.us;                           // :268
+    const T den = t_max(rm - L.r, DHTS_EPS);
+    const T lam0m_r = R.us - T(0.5) * umax * ((rm >= DHTS_EPS) ? t_abs(b) : rm * DHTS_RSQRT_EPS);
+    const T s_vac = (lam0l + L.w) * T(0.5);                        // :247, :315
+    const T s_rare = (lam0l + lam0m_r) * T(0.5);                   // :292
+    const bool l0 = lam0l >= T(0);
+    // outcome index per branch, then the first matching branch wins
+    const int c_vac = l0 ? 0 : 2;
+    const int c_shock = (fd >= T(0)) ? 0 : 1;
+    const int c_rare = l0 ? 0 : ((lam0m_r <= T(0)) ? 1 : 2);
+    const int c_tail = shock ? c_shock : (rare ? c_rare : c_vac);
+    o.cas = vacL ? 0 : (vacR ? c_vac : (same ? 0 : c_tail));
+    // wave speeds for the CFL test (_macro_lane.py:137-146)
+    const bool use_shock = !vacL && !vacR && !same && shock;
+    const T s0 = (vacL || (!vacR && same)) ? T(0) : (vacR ? s_vac : (rare ? s_rare : s_vac));
+    const T s1 = vacL ? L.us : (vacR ? s_vac : R.us);
+    const bool ok1 = dt * t_max(t_abs(s1), T(1e-5)) < dx;
+    const bool ok0s = dt * t_max(t_abs(fd), T(1e-5) * den) < dx * den;
+    const bool ok0n = dt * t_max(t_abs(s0), T(1e-5)) < dx;
+    o.cfl_bad = !((use_shock ? ok0s : ok0n) && ok1);
+    // selected state: Q_L (:155-165), Q_M (:186-199) or Q_C (:168-183)
+    const T sc = L.us + umax * L.sq;
+    const T q = sc * inv15;
+    const bool isL = o.cas == 0, isM = o.cas == 1;
+    const T root = isM ? b : q;
+    o.rootr = isL ? L.sq : t_abs(root);
+    o.r0 = isL ? L.r : root * root;
+    o.u0 = isL ? L.uc : (isM ? R.us : (T(0.5) / T(1.5)) * sc);
+    const T ueq_new = umax * (T(1) - f_sqrt_pos(root * root + DHTS_EPS));
+    o.ueq0 = isL ? L.uf : ueq_new;
+    o.y0 = isL ? L.y : o.r0 * (o.u0 - ueq_new);
     return o;
 }
 
@@ -159,59 +182,53 @@ __device__ __forceinline__ Riem<T> riemann(const Cell<T>& L, const Cell<T>& R, T
 template <typename T>
 __device__ __forceinline__ void riemann_adj(const Cell<T>& L, const Cell<T>& R, const Riem<T>& s, T umax, T inv_umax,
                                             T inv15, T wr, T wy, T& par, T& pay, T& pbr, T& pby) {
+    const bool isL = s.cas == 0, isM = s.cas == 1;
     // flux_prime at Q0 (darz.py:217-233), transposed and applied to w
-    T rr, inv_sq, inv_rr;
-    if (s.cas == 0) { rr = t_max(s.r0, DHTS_EPS); inv_sq = L.rs; inv_rr = L.ri; }
-    else {
-        bool big = s.r0 >= DHTS_EPS;
-        rr = big ? s.r0 : DHTS_EPS;
-        inv_sq = big ? T(1) / s.rootr : DHTS_RSQRT_EPS;
-        inv_rr = inv_sq * inv_sq;
-    }
-    T ueqp0 = T(-0.5) * umax * inv_sq;                 // u_eq'(max(r0,eps))  _arz.py:146-149
-    T yr = s.y0 * inv_rr;
-    T f00 = s.ueq0 + rr * ueqp0;
-    T f10 = s.y0 * ueqp0 - yr * yr;
-    T f11 = T(2) * yr + s.ueq0;
-    T z0 = f00 * wr + f10 * wy;
-    T z1 = wr + f11 * wy;
-    if (s.cas == 0) {                                  // dL = I, dR = 0      darz.py:12-33
-        par = z0; pay = z1; pbr = T(0); pby = T(0);
-        return;
-    }
-    T ueqpL = T(-0.5) * umax * L.rs;
-    T duL_drL = -L.y * L.ri * L.ri + ueqpL;
-    T duL_dyL = L.ri;
-    if (s.cas == 1) {                                  // compute_dM          darz.py:35-122
-        T ueqpR = T(-0.5) * umax * R.rs;
-        T duR_drR = -R.y * R.ri * R.ri + ueqpR;
-        T duR_dyR = R.ri;
-        T a = T(2) * s.rootr;                          // (1/gamma) rM^(1-gamma)
-        T drM_drL = a * (T(0.5) * L.rs + duL_drL * inv_umax);
-        T drM_dyL = a * (duL_dyL * inv_umax);
-        T k = (s.u0 - s.ueq0) - s.r0 * ueqp0;          // e - rM u_eq'(rM)
-        T dyM_drL = drM_drL * k;
-        T dyM_dyL = drM_dyL * k;
-        T drM_drR = -a * (duR_drR * inv_umax);
-        T drM_dyR = -a * (duR_dyR * inv_umax);
-        T dyM_drR = drM_drR * k + s.r0 * duR_drR;
-        T dyM_dyR = drM_dyR * k + s.r0 * duR_dyR;
-        par = drM_drL * z0 + dyM_drL * z1; pay = drM_dyL * z0 + dyM_dyL * z1;
-        pbr = drM_drR * z0 + dyM_drR * z1; pby = drM_dyR * z0 + dyM_dyR * z1;
-    } else {                                           // compute_dC          darz.py:124-192
-        const T g13 = T(0.5) / T(1.5);
-        T f = umax * T(0.5) * L.rs;
-        T duC_drL = g13 * (duL_drL + f);
-        T duC_dyL = g13 * duL_dyL;
-        T e = T(2) * s.rootr * inv15;                  // rC^(1-gamma) / gamma / ((gamma+1) u_max)
-        T drC_drL = e * (duL_drL + f);
-        T drC_dyL = e * duL_dyL;
-        T g = s.u0 - s.ueq0;
-        T dyC_drL = drC_drL * g + s.r0 * (duC_drL - ueqp0 * drC_drL);
-        T dyC_dyL = drC_dyL * g + s.r0 * (duC_dyL - ueqp0 * drC_dyL);
-        par = drC_drL * z0 + dyC_drL * z1; pay = drC_dyL * z0 + dyC_dyL * z1;
-        pbr = T(0); pby = T(0);
-    }
+    const bool big = s.r0 >= DHTS_EPS;
+    const T rr = t_max(s.r0, DHTS_EPS);
+    const T inv_root = f_rcp(t_max(s.rootr, T(1e-30)));
+    const T inv_sq = isL ? L.rs : (big ? inv_root : DHTS_RSQRT_EPS);
+    const T inv_rr = isL ? L.ri : inv_sq * inv_sq;
+    const T ueqp0 = T(-0.5) * umax * inv_sq;                 // u_eq'(max(r0,eps))  _arz.py:146-149
+    const T yr = s.y0 * inv_rr;
+    const T f00 = s.ueq0 + rr * ueqp0;
+    const T f10 = s.y0 * ueqp0 - yr * yr;
+    const T f11 = T(2) * yr + s.ueq0;
+    const T z0 = f00 * wr + f10 * wy;
+    const T z1 = wr + f11 * wy;
+    // shared pieces of dM (darz.py:35-122) and dC (darz.py:124-192)
+    const T ueqpL = T(-0.5) * umax * L.rs;
+    const T duL_drL = -L.y * L.ri * L.ri + ueqpL;
+    const T duL_dyL = L.ri;
+    const T ueqpR = T(-0.5) * umax * R.rs;
+    const T duR_drR = -R.y * R.ri * R.ri + ueqpR;
+    const T duR_dyR = R.ri;
+    const T a = T(2) * s.rootr;                              // (1/gamma) r0^(1-gamma)
+    const T g = s.u0 - s.ueq0;
+    const T k = g - s.r0 * ueqp0;
+    // Q_M
+    const T drM_drL = a * (T(0.5) * L.rs + duL_drL * inv_umax);
+    const T drM_dyL = a * (duL_dyL * inv_umax);
+    const T drM_drR = -a * (duR_drR * inv_umax);
+    const T drM_dyR = -a * (duR_dyR * inv_umax);
+    const T dyM_drR = drM_drR * k + s.r0 * duR_drR;
+    const T dyM_dyR = drM_dyR * k + s.r0 * duR_dyR;
+    // Q_C
+    const T g13 = T(0.5) / T(1.5);
+    const T f = umax * T(0.5) * L.rs;
+    const T e = a * inv15;                                   // rC^(1-gamma) / gamma / ((gamma+1) u_max)
+    const T drC_drL = e * (duL_drL + f);
+    const T drC_dyL = e * duL_dyL;
+    const T dyC_drL = drC_drL * k + s.r0 * (g13 * (duL_drL + f));
+    const T dyC_dyL = drC_dyL * k + s.r0 * (g13 * duL_dyL);
+    // d Q0 / d Q_left (2x2) and d Q0 / d Q_right, selected by outcome (Q_L: identity / zero, darz.py:12-33)
+    const T d00 = isL ? T(1) : (isM ? drM_drL : drC_drL);
+    const T d01 = isL ? T(0) : (isM ? drM_dyL : drC_dyL);
+    const T d10 = isL ? T(0) : (isM ? drM_drL * k : dyC_drL);
+    const T d11 = isL ? T(1) : (isM ? drM_dyL * k : dyC_dyL);
+    par = d00 * z0 + d10 * z1; pay = d01 * z0 + d11 * z1;
+    pbr = isM ? (drM_drR * z0 + dyM_drR * z1) : T(0);
+    pby = isM ? (drM_dyR * z0 + dyM_dyR * z1) : T(0);
 }
 
 // d compute_u / d(r, y) as autograd differentiates set_r_y OUTSIDE the
