@@ -190,8 +190,8 @@ __device__ __forceinline__ bool chunk_fwd_step(T* r, T* y, const T* u_first, boo
     return bad && active;
 }
 
-template <typename T, int C>
-__global__ void arz_rollout_fwd_reg_kernel(const T* __restrict__ r0, const T* __restrict__ y0,
+template <typename T, int C, int MB>
+__global__ void __launch_bounds__(1024 / C, MB) arz_rollout_fwd_reg_kernel(const T* __restrict__ r0, const T* __restrict__ y0,
                                            const T* __restrict__ u0, const T* __restrict__ ghost,
                                            const T* __restrict__ dx, const T* __restrict__ umax_, T dt, int B, int N,
                                            int steps, int K, int lpc, T* __restrict__ ckpt, T* __restrict__ rT,
@@ -236,8 +236,8 @@ __global__ void arz_rollout_fwd_reg_kernel(const T* __restrict__ r0, const T* __
     if (bad) atomicOr(flags, FLAG_CFL);
 }
 
-template <typename T, int C>
-__global__ void arz_rollout_bwd_reg_kernel(const T* __restrict__ ckpt, const T* __restrict__ u0,
+template <typename T, int C, int MB>
+__global__ void __launch_bounds__(1024 / C, MB) arz_rollout_bwd_reg_kernel(const T* __restrict__ ckpt, const T* __restrict__ u0,
                                            const T* __restrict__ ghost, const T* __restrict__ dx,
                                            const T* __restrict__ umax_, T dt, int B, int N, int steps, int K, int lpc,
                                            const T* __restrict__ rT, const T* __restrict__ yT,
@@ -359,7 +359,7 @@ __global__ void arz_rollout_bwd_reg_kernel(const T* __restrict__ ckpt, const T* 
 
 // ------------------------------------------------------------------ host-side planning and launch
 
-struct RegPlan { int C, lpc, threads, grid; size_t smem; };
+struct RegPlan { int C, lpc, threads, grid, mb; size_t smem; };
 
 static int round32(int x) { return (x + 31) / 32 * 32; }
 
@@ -373,14 +373,18 @@ static int sm_count_r() {
     return n;
 }
 
-template <typename T> static int plan_reg(int B, int N, RegPlan* p) {
-    int C = (N % 4 == 0) ? 4 : ((N % 2 == 0) ? 2 : 1);
+// Measured on B200 (profiles/r1c): forward is fastest with 4 cells per thread capped at 128 registers
+// (2 CTAs of 256 threads per SM); the adjoint holds more live state and is fastest with 2 cells per thread.
+template <typename T> static int plan_reg(int B, int N, bool adj, RegPlan* p) {
+    int want = adj ? 2 : 4;
     if (const char* e = getenv("DHTS_ARZ_C")) {      // tuning knob: cells per thread (must divide N)
         int c = atoi(e);
-        if ((c == 1 || c == 2 || c == 4) && N % c == 0) C = c;
+        if (c == 1 || c == 2 || c == 4) want = c;
     }
+    int C = (want >= 4 && N % 4 == 0) ? 4 : ((want >= 2 && N % 2 == 0) ? 2 : 1);
     int tpl = N / C;
-    if (tpl > 1024) return DHTS_ERR_UNSUPPORTED;
+    if (tpl > 1024 / C && C > 1) { C = (N % 4 == 0) ? 4 : C; tpl = N / C; }   // long lanes: widest chunk that divides N
+    if (tpl > 1024 / C) return DHTS_ERR_UNSUPPORTED;
     const int target = 256;                       // threads per CTA when lanes are short
     int lpc = tpl >= target ? 1 : target / tpl;
     if (lpc > B) lpc = B;
@@ -388,11 +392,17 @@ template <typename T> static int plan_reg(int B, int N, RegPlan* p) {
     p->C = C; p->lpc = lpc; p->threads = round32(lpc * tpl);
     p->smem = shm_bytes<T>(lpc, p->threads / 32);
     p->grid = (B + lpc - 1) / lpc;
+    p->mb = adj ? 1 : 2;
+    if (const char* e = getenv("DHTS_ARZ_MB")) p->mb = atoi(e) == 2 ? 2 : 1;
     return DHTS_OK;
 }
 
-#define DHTS_C_DISPATCH(Cval, CALL) \
-    if (Cval == 4) { CALL(4) } else if (Cval == 2) { CALL(2) } else { CALL(1) }
+#define DHTS_C_DISPATCH(P, CALL)                                                                     \
+    if ((P).mb == 2) {                                                                               \
+        if ((P).C == 4) { CALL(4, 2) } else if ((P).C == 2) { CALL(2, 2) } else { CALL(1, 1) }       \
+    } else {                                                                                         \
+        if ((P).C == 4) { CALL(4, 1) } else if ((P).C == 2) { CALL(2, 1) } else { CALL(1, 1) }       \
+    }
 
 static int status_r() { return cudaGetLastError() == cudaSuccess ? DHTS_OK : DHTS_ERR_CUDA; }
 
@@ -404,20 +414,20 @@ static int rollout_fwd(const T* r0, const T* y0, const T* u0, const T* ghost, co
     if (ckpt && K < 1) return DHTS_ERR_INVALID;
     if (B == 0) return DHTS_OK;
     RegPlan p;
-    int rc = plan_reg<T>(B, N, &p);
+    int rc = plan_reg<T>(B, N, false, &p);
     if (rc) return rc;
     if (K < 1) K = 1;
     int grid = p.grid;
-#define CALL(CC) arz_rollout_fwd_reg_kernel<T, CC><<<grid, p.threads, p.smem, st>>>(r0, y0, u0, ghost, dx, umax, dt, B, N, steps, K, p.lpc, ckpt, rT, yT, uT, flags);
-    DHTS_C_DISPATCH(p.C, CALL)
+#define CALL(CC, MB) arz_rollout_fwd_reg_kernel<T, CC, MB><<<grid, p.threads, p.smem, st>>>(r0, y0, u0, ghost, dx, umax, dt, B, N, steps, K, p.lpc, ckpt, rT, yT, uT, flags);
+    DHTS_C_DISPATCH(p, CALL)
 #undef CALL
     return status_r();
 }
 
 template <typename T> static int bwd_grid_r(const RegPlan& p) {
     int occ = 0;
-#define CALL(CC) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, arz_rollout_bwd_reg_kernel<T, CC>, p.threads, p.smem);
-    DHTS_C_DISPATCH(p.C, CALL)
+#define CALL(CC, MB) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, arz_rollout_bwd_reg_kernel<T, CC, MB>, p.threads, p.smem);
+    DHTS_C_DISPATCH(p, CALL)
 #undef CALL
     if (occ < 1) occ = 1;
     long long g = (long long)sm_count_r() * occ;
@@ -427,7 +437,7 @@ template <typename T> static int bwd_grid_r(const RegPlan& p) {
 template <typename T> static long long rollout_scratch_elems(int B, int N, int K) {
     RegPlan p;
     if (B <= 0) return 0;
-    if (K < 1 || plan_reg<T>(B, N, &p)) return -1;
+    if (K < 1 || plan_reg<T>(B, N, true, &p)) return -1;
     return (long long)bwd_grid_r<T>(p) * K * 2 * p.lpc * N;
 }
 
@@ -441,12 +451,12 @@ static int rollout_bwd(const T* ckpt, const T* u0, const T* ghost, const T* dx, 
     if (g_uT && (!rT || !yT)) return DHTS_ERR_INVALID;
     if (B == 0) return DHTS_OK;
     RegPlan p;
-    int rc = plan_reg<T>(B, N, &p);
+    int rc = plan_reg<T>(B, N, true, &p);
     if (rc) return rc;
     int grid = bwd_grid_r<T>(p);
     if ((long long)grid * K * 2 * p.lpc * N > scratch_elems) return DHTS_ERR_INVALID;
-#define CALL(CC) arz_rollout_bwd_reg_kernel<T, CC><<<grid, p.threads, p.smem, st>>>(ckpt, u0, ghost, dx, umax, dt, B, N, steps, K, p.lpc, rT, yT, g_rT, g_yT, g_uT, scratch, g_r0, g_y0, g_ghost, flags);
-    DHTS_C_DISPATCH(p.C, CALL)
+#define CALL(CC, MB) arz_rollout_bwd_reg_kernel<T, CC, MB><<<grid, p.threads, p.smem, st>>>(ckpt, u0, ghost, dx, umax, dt, B, N, steps, K, p.lpc, rT, yT, g_rT, g_yT, g_uT, scratch, g_r0, g_y0, g_ghost, flags);
+    DHTS_C_DISPATCH(p, CALL)
 #undef CALL
     return status_r();
 }

@@ -30,7 +30,7 @@ template <> __device__ __forceinline__ float t_sqrt<float>(float x) { return sqr
 template <typename T> __device__ __forceinline__ T t_abs(T x) { return x < T(0) ? -x : x; }
 
 // Branch-free 1/sqrt(x) and 1/x for well-scaled positive x (densities, gaps): hardware
-// approximation (MUFU.RSQ64H / MUFU.RCP64H, ~2^-22) refined to ~1 ulp.  The library
+// approximation (MUFU.RSQ64H / MUFU.RCP64H, ~2^-22) refined by one cubic step to ~1 ulp.  The library
 // sqrt()/division carry special-case slow paths and long dependent Newton chains that
 // dominated the stall profile (profiles/r1a, r1b); parity has >6 digits of headroom.
 template <typename T> __device__ __forceinline__ T f_rsqrt(T x);
@@ -38,9 +38,7 @@ template <> __device__ __forceinline__ double f_rsqrt<double>(double x) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     double e = fma(-(x * y), y, 1.0);                 // 1 - x y^2
-    y = fma(y, e * fma(0.375, e, 0.5), y);            // Halley: error^3
-    e = fma(-(x * y), y, 1.0);
-    return fma(y * 0.5, e, y);                        // Newton polish
+    return fma(y, e * fma(0.375, e, 0.5), y);         // Halley step: error^3 -> below 1 ulp
 }
 template <> __device__ __forceinline__ float f_rsqrt<float>(float x) { return rsqrtf(x); }
 template <typename T> __device__ __forceinline__ T f_rcp(T x);
@@ -48,9 +46,7 @@ template <> __device__ __forceinline__ double f_rcp<double>(double x) {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     double e = fma(-x, y, 1.0);
-    y = fma(y, fma(e, e, e), y);                      // y (1 + e + e^2)
-    e = fma(-x, y, 1.0);
-    return fma(y, e, y);
+    return fma(y, fma(e, e, e), y);                   // y (1 + e + e^2): error^3 -> below 1 ulp
 }
 template <> __device__ __forceinline__ float f_rcp<float>(float x) { return __frcp_rn(x); }
 // sqrt(x) = x * rsqrt(x) with one correction step (x > 0)
