@@ -339,9 +339,13 @@ def run_ours(a):
         # dominant kernel: arz_rollout_bwd (one launch per pass per GPU)
         bwd_bytes = B * N * T * ARZ_SCALARS_BWD * esz
         bwd_s = arz_bwd / K / 1e3
+        # DRAM bytes of the same kernel from the committed `ncu --set full` capture (profiles/traffic.json, written
+        # by scripts/ncu_summary.py): captured on a smaller batch with the same checkpoint interval, so it is
+        # carried per cell-step and scaled to this launch
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("arz_rollout_bwd_" + a.dtype)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("arz_rollout_bwd_" + a.dtype)
+            traffic = tj["dram_bytes_per_cell_step"] * B * N * T
         except Exception:
             pass
         both_bytes = B * N * T * (ARZ_SCALARS_FWD + ARZ_SCALARS_BWD) * esz
