@@ -57,13 +57,11 @@ def flags():
 def check_flags():
     """Maps the device-side conditions to the reference's conventions (CFL / NaN-gradient
     AssertionError, collision print-and-continue) and clears them."""
-    f = _flags.get(device()) if torch.cuda.is_available() else None
-    if f is None:
-        return
-    try:
-        f.check()
-    finally:
-        f.reset()
+    for f in _flags.values():
+        try:
+            f.check()
+        finally:
+            f.reset()
 
 
 def is_tensor(x) -> bool:
