@@ -54,7 +54,8 @@ class ArzStepFn(torch.autograd.Function):
             check(_fn("arz_step_fwd", r_pad.dtype)(ptr(r_pad), ptr(y_pad), ptr(u_pad), ptr(ueq_pad), ptr(dx), ptr(umax),
                                                    creal(r_pad.dtype, dt_), B, N, ptr(nr), ptr(ny), ptr(nu), ptr(case),
                                                    ptr(flags), stream_ptr(dev)), "dhts_arz_step_fwd")
-        ctx.save_for_backward(r_pad, y_pad, u_pad, ueq_pad, dx, umax, nr, ny, flags)
+        ctx.save_for_backward(r_pad, y_pad, u_pad, ueq_pad, dx, umax, nr, ny)
+        ctx.flags = flags          # written in place by kernels and reset by the host: not a versioned autograd input
         ctx.dt = dt_
         ctx.mark_non_differentiable(*([case] if want_case else []))
         if want_case:
@@ -63,7 +64,8 @@ class ArzStepFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_nr, g_ny, g_nu, *_):
-        r_pad, y_pad, u_pad, ueq_pad, dx, umax, nr, ny, flags = ctx.saved_tensors
+        r_pad, y_pad, u_pad, ueq_pad, dx, umax, nr, ny = ctx.saved_tensors
+        flags = ctx.flags
         dev = r_pad.device
         B, P = r_pad.shape
         z = lambda g: torch.zeros_like(nr) if g is None else g.contiguous()
@@ -97,13 +99,15 @@ class ArzRolloutFn(torch.autograd.Function):
                                                    creal(r0.dtype, dt_), B, N, steps, K, ptr(ckpt), ptr(rT), ptr(yT),
                                                    ptr(uT), ptr(flags), stream_ptr(dev)), "dhts_arz_rollout_fwd")
         if need_grad:
-            ctx.save_for_backward(ckpt, u0, ghost, dx, umax, rT, yT, flags)
+            ctx.save_for_backward(ckpt, u0, ghost, dx, umax, rT, yT)
+        ctx.flags = flags
         ctx.cfg = (dt_, steps, K, B, N)
         return rT, yT, uT
 
     @staticmethod
     def backward(ctx, g_rT, g_yT, g_uT):
-        ckpt, u0, ghost, dx, umax, rT, yT, flags = ctx.saved_tensors
+        ckpt, u0, ghost, dx, umax, rT, yT = ctx.saved_tensors
+        flags = ctx.flags
         dt_, steps, K, B, N = ctx.cfg
         dev, dtype = ghost.device, ghost.dtype
         g_rT, g_yT, g_uT = map(_c, (g_rT, g_yT, g_uT))
@@ -149,7 +153,8 @@ class IdmStepFn(torch.autograd.Function):
             check(_fn("idm_step_fwd", p.dtype)(ptr(p), ptr(v), ptr(params), ptr(lane_off), ptr(veh_lane), ptr(head),
                                                creal(p.dtype, dt_), V, L, ptr(np_), ptr(nv_), ptr(vf), ptr(flags),
                                                stream_ptr(dev)), "dhts_idm_step_fwd")
-        ctx.save_for_backward(p, v, head, params, lane_off, veh_lane, flags)
+        ctx.save_for_backward(p, v, head, params, lane_off, veh_lane)
+        ctx.flags = flags
         ctx.dt = dt_
         if want_flags:
             ctx.mark_non_differentiable(vf)
@@ -158,7 +163,8 @@ class IdmStepFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_np, g_nv, *_):
-        p, v, head, params, lane_off, veh_lane, flags = ctx.saved_tensors
+        p, v, head, params, lane_off, veh_lane = ctx.saved_tensors
+        flags = ctx.flags
         dev = p.device
         V, L = p.numel(), lane_off.numel() - 1
         z = lambda g: torch.zeros_like(p) if g is None else g.contiguous()
@@ -193,13 +199,15 @@ class IdmRolloutFn(torch.autograd.Function):
                                                    ptr(pT), ptr(vT), ptr(flags), stream_ptr(dev)),
                   "dhts_idm_rollout_fwd")
         if need_grad:
-            ctx.save_for_backward(ckpt, head, params, lane_off, flags)
+            ctx.save_for_backward(ckpt, head, params, lane_off)
+        ctx.flags = flags
         ctx.cfg = (dt_, steps, K, V, L, int(max_lane))
         return pT, vT
 
     @staticmethod
     def backward(ctx, g_pT, g_vT):
-        ckpt, head, params, lane_off, flags = ctx.saved_tensors
+        ckpt, head, params, lane_off = ctx.saved_tensors
+        flags = ctx.flags
         dt_, steps, K, V, L, max_lane = ctx.cfg
         dev, dtype = head.device, head.dtype
         z = lambda g: torch.zeros((V,), dtype=dtype, device=dev) if g is None else g.contiguous()

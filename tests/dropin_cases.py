@@ -160,7 +160,8 @@ def case_hybrid_chain_spawn_absorb_and_gradients(tier, precision, dtype, tol_s, 
     for k in range(3):
         assert relerr(s0[k].detach(), g["lane0"][k]) < tol_s * 5, ("lane0", k)
         assert relerr(s2[k].detach(), g["lane2"][k]) < tol_s * 5, ("lane2", k)
-    veh = np.array([[float(mv.position), float(mv.speed), float(mv.a)] for mv in l1.curr_vehicle]).reshape(-1, 3)
+    fl = lambda x: float(x.detach()) if th.is_tensor(x) else float(x)
+    veh = np.array([[fl(mv.position), fl(mv.speed), fl(mv.a)] for mv in l1.curr_vehicle]).reshape(-1, 3)
     assert veh.shape == g["veh"].shape and relerr(veh, g["veh"]) < tol_s * 5
     loss = (s2[0] * t(g["w_r"])).sum() + (s2[2] * t(g["w_u"])).sum()
     w_veh = g["w_veh"]
