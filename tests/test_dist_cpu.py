@@ -1,0 +1,75 @@
+"""world_size-2 gloo test of the shard / reduce harness (dhts_b200.dist): the host-side logic of the N>1 path.
+Each rank 'simulates' its lane shard with a deterministic per-lane function (the kernels need a GPU; what is tested
+here is partitioning, CSR re-basing, the loss / shared-gradient reductions and lane-ordered gathering)."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as td
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _lane_fn(r, w):
+    return (r * r).sum(dim=1) * w          # stands for a per-lane rollout loss with a shared parameter w
+
+
+def _worker(rank, ws, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    td.init_process_group("gloo", rank=rank, world_size=ws)
+    from dhts_b200 import dist
+    g = torch.Generator().manual_seed(3)
+    B, N = 7, 5                                                   # uneven split on purpose: 4 + 3
+    r = torch.rand((B, N), generator=g, dtype=torch.float64)
+    sizes = torch.tensor([3, 0, 4, 1, 2, 6, 0, 5, 2])             # ragged micro lanes incl. empty ones
+    off = torch.cat([torch.zeros(1, dtype=torch.int64), sizes.cumsum(0)]).to(torch.int32)
+    V = int(off[-1])
+    p = torch.arange(V, dtype=torch.float64); par = torch.arange(6 * V, dtype=torch.float64).reshape(6, V)
+    head = torch.arange(2 * 9, dtype=torch.float64).reshape(9, 2)
+    w = torch.tensor(0.5, dtype=torch.float64, requires_grad=True)
+    (r_loc,) = dist.shard_lanes([r], rank, ws)
+    off_loc, (p_loc, par_loc), (head_loc,) = dist.shard_csr(off, [p, par], [head], rank, ws)
+    lane_loss = _lane_fn(r_loc, w)
+    lane_loss.sum().backward()
+    total = dist.reduce_losses(lane_loss.sum(), p_loc.sum())
+    dist.reduce_shared_grads([w])
+    gathered = dist.gather_lanes(lane_loss.detach(), B)
+    lo, hi = dist.shard_range(9, rank, ws)
+    q.put((rank, total.tolist(), float(w.grad), gathered.tolist(), off_loc.tolist(), p_loc.tolist(),
+           par_loc.shape[1], head_loc.tolist(), (lo, hi)))
+    td.destroy_process_group()
+
+
+def test_two_rank_shards_reduce_to_the_unsharded_result():
+    sys.path.insert(0, ROOT)
+    from dhts_b200 import dist
+    ws, port = 2, 29500 + os.getpid() % 2000
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, ws, port, q)) for r in range(ws)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(ws))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    # unsharded truth
+    g = torch.Generator().manual_seed(3)
+    r = torch.rand((7, 5), generator=g, dtype=torch.float64)
+    w = torch.tensor(0.5, dtype=torch.float64, requires_grad=True)
+    full = _lane_fn(r, w); full.sum().backward()
+    sizes = [3, 0, 4, 1, 2, 6, 0, 5, 2]
+    V = sum(sizes)
+    for rank, total, wgrad, gathered, off_loc, p_loc, npar, head_loc, (lo, hi) in res:
+        assert abs(total[0] - float(full.detach().sum())) < 1e-12 and total[1] == V * (V - 1) / 2
+        assert abs(wgrad - float(w.grad)) < 1e-12
+        assert gathered == full.detach().tolist()          # bitwise, in lane order
+        assert off_loc[0] == 0 and off_loc[-1] == len(p_loc) == npar
+        assert [b - a for a, b in zip(off_loc, off_loc[1:])] == sizes[lo:hi]
+        assert head_loc == [[2.0 * l, 2.0 * l + 1] for l in range(lo, hi)]
+    assert res[0][5] + res[1][5] == [float(i) for i in range(V)]          # vehicle slices tile the batch in order
+    assert [dist.shard_range(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    assert dist.world() == (0, 1)
