@@ -135,8 +135,7 @@ def cpu_port_rates(a, seconds_budget=12.0):
     lanes of the config's shape (N cells / n vehicles), fewer lanes and fewer steps.  Returns rates + sample text."""
     import numpy as np
     from oracle import oracle as O
-    cores = len(os.sched_getaffinity(0))
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    cores = O.set_threads(len(os.sched_getaffinity(0)))     # explicit: torchrun exports OMP_NUM_THREADS=1
     rng = np.random.default_rng(SEED)
     N, n, umax = a.cells, a.lane_vehicles, 30.0
 

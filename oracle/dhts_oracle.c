@@ -27,6 +27,20 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* Thread count of the lane-parallel rollouts (bench.py CPU arms); returns what is in effect (1 without OpenMP). */
+int orc_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
 
 #define GAMMA 0.5      /* model/macro/_arz.py:1 */
 #define EPSILON 1e-5   /* model/macro/_arz.py:2 */

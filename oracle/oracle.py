@@ -55,6 +55,11 @@ def lib():
     return _lib
 
 
+def set_threads(n: int) -> int:
+    """OpenMP threads of the lane-parallel rollouts; returns the count in effect (torchrun exports OMP_NUM_THREADS=1)."""
+    return int(lib().orc_set_threads(int(n)))
+
+
 def _d(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
