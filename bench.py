@@ -42,7 +42,10 @@ def parse():
     ap.add_argument("--micro-lanes", type=int, default=65536, help="IDM lanes per GPU")
     ap.add_argument("--lane-vehicles", type=int, default=64)
     ap.add_argument("--sim-steps", type=int, default=1000)
-    ap.add_argument("--ckpt-every", type=int, default=32)
+    ap.add_argument("--ckpt-every", type=int, default=0,
+                    help="ARZ checkpoint interval; 0 = auto: store every state (no recompute in the adjoint) and walk "
+                         "the lanes in chunks that fit the free HBM, else 32 with segment recompute")
+    ap.add_argument("--idm-ckpt-every", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -232,28 +235,48 @@ def run_ours(a):
     V = a.micro_lanes * a.lane_vehicles
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
+    # ARZ plan: lanes per chunk and checkpoint interval (functional.arz_rollout_plan: every state stored when a
+    # chunk of >= 296 lanes fits the free HBM, which removes the segment recompute from the adjoint)
+    if a.ckpt_every > 0:
+        arz_K = a.ckpt_every
+        arz_chunk = F.arz_rollout_plan(B, N, T, dt_t, dev)[0] if arz_K == 1 else B
+    else:
+        arz_chunk, arz_K = F.arz_rollout_plan(B, N, T, dt_t, dev)
+    arz_chunks = [(lo, min(B, lo + arz_chunk)) for lo in range(0, B, arz_chunk)]
+    # one checkpoint arena for all chunks and passes (a chunk's checkpoints are dead once its adjoint has run)
+    arz_arena = torch.empty(((T + arz_K - 1) // arz_K) * 2 * arz_chunk * N, dtype=dt_t, device=dev)
+
     def arz_pass(d, timers=None):
-        r0 = d["r0"].detach().requires_grad_(); u0 = d["u0"].detach().requires_grad_()
-        if timers: timers[0].record()
-        rT, yT, uT = F.arz_rollout(r0, u0, d["gr"], d["gu"], A["dx"], A["umax"], A["dt"], T, ckpt_every=a.ckpt_every,
-                                   flags=flags)
-        if timers: timers[1].record()
-        loss = ((rT - d["tr"]) ** 2).sum() + ((uT - d["tu"]) ** 2).sum()     # example/inverse/macro.py:226-241
-        if timers: timers[2].record()
-        loss.backward()
-        if timers: timers[3].record()
-        return loss.detach(), r0.grad, u0.grad
+        """fwd + loss + adjoint of all B lanes, chunk of lanes by chunk of lanes (lanes are independent)."""
+        g_r0 = torch.empty_like(d["r0"]); g_u0 = torch.empty_like(d["u0"])
+        total = torch.zeros((), dtype=dt_t, device=dev)
+        for lo, hi in arz_chunks:
+            r0 = d["r0"][lo:hi].detach().requires_grad_(); u0 = d["u0"][lo:hi].detach().requires_grad_()
+            ev4 = [ev() for _ in range(4)] if timers is not None else None
+            if ev4: ev4[0].record()
+            rT, yT, uT = F.arz_rollout(r0, u0, d["gr"][lo:hi], d["gu"][lo:hi], A["dx"], A["umax"], A["dt"], T,
+                                       ckpt_every=arz_K, flags=flags, ckpt_buffer=arz_arena)
+            if ev4: ev4[1].record()
+            loss = ((rT - d["tr"][lo:hi]) ** 2).sum() + ((uT - d["tu"][lo:hi]) ** 2).sum()   # example/inverse/macro.py:226-241
+            if ev4: ev4[2].record()
+            loss.backward()
+            if ev4: ev4[3].record(); timers.append(ev4)
+            g_r0[lo:hi] = r0.grad; g_u0[lo:hi] = u0.grad
+            total += loss.detach()
+            del rT, yT, uT, loss, r0, u0
+        return total, g_r0, g_u0
 
     def idm_pass(d, timers=None):
         p0 = d["p0"].detach().requires_grad_(); v0 = d["v0"].detach().requires_grad_()
-        if timers: timers[0].record()
-        pT, vT = F.idm_rollout(p0, v0, d["params"], d["off"], d["head"], M["dt"], T, ckpt_every=a.ckpt_every,
+        ev4 = [ev() for _ in range(4)] if timers is not None else None
+        if ev4: ev4[0].record()
+        pT, vT = F.idm_rollout(p0, v0, d["params"], d["off"], d["head"], M["dt"], T, ckpt_every=a.idm_ckpt_every,
                                flags=flags, max_lane=M["n"])
-        if timers: timers[1].record()
+        if ev4: ev4[1].record()
         loss = ((pT - d["tp"]) ** 2).sum() + ((vT - d["tv"]) ** 2).sum()     # example/inverse/micro.py:221-236
-        if timers: timers[2].record()
+        if ev4: ev4[2].record()
         loss.backward()
-        if timers: timers[3].record()
+        if ev4: ev4[3].record(); timers.append(ev4)
         return loss.detach(), p0.grad, v0.grad
 
     def reduce_loss(la, li):
@@ -270,12 +293,11 @@ def run_ours(a):
     barrier()
     clocks = Clocks(local) if rank == 0 else None
     t_wall0 = time.time()
-    tA = [[ev() for _ in range(4)] for _ in range(a.steps)]
-    tM = [[ev() for _ in range(4)] for _ in range(a.steps)]
+    tA, tM = [], []              # CUDA events (start, fwd done, loss done, bwd done) per launch pair
     e0, e1 = ev(), ev()
     e0.record()
     for s in range(a.steps):
-        la, _, _ = arz_pass(devA, tA[s]); li, _, _ = idm_pass(devM, tM[s]); losses = reduce_loss(la, li)
+        la, _, _ = arz_pass(devA, tA); li, _, _ = idm_pass(devM, tM); losses = reduce_loss(la, li)
     e1.record()
     barrier()
     t_wall1 = time.time()
@@ -334,15 +356,17 @@ def run_ours(a):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6650 GB/s (of fallback)"
         # dominant kernel: arz_rollout_bwd (one launch per pass per GPU)
-        bwd_bytes = B * N * T * ARZ_SCALARS_BWD * esz
-        bwd_s = arz_bwd / K / 1e3
+        nl = len(arz_chunks)                                   # adjoint launches per pass (one per lane chunk)
+        bwd_bytes = B * N * T * ARZ_SCALARS_BWD * esz / nl      # algorithmic bytes of ONE launch (average chunk)
+        bwd_s = arz_bwd / K / nl / 1e3                         # average duration of one launch
         # DRAM bytes of the same kernel from the committed `ncu --set full` capture (profiles/traffic.json, written
         # by scripts/ncu_summary.py): captured on a smaller batch with the same checkpoint interval, so it is
         # carried per cell-step and scaled to this launch
         traffic = None
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("arz_rollout_bwd_" + a.dtype)
-            traffic = tj["dram_bytes_per_cell_step"] * B * N * T
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            tj = tj.get("arz_rollout_bwd_%s_k%d" % (a.dtype, arz_K)) or tj["arz_rollout_bwd_" + a.dtype]
+            traffic = tj["dram_bytes_per_cell_step"] * B * N * T / len(arz_chunks)
         except Exception:
             pass
         both_bytes = B * N * T * (ARZ_SCALARS_FWD + ARZ_SCALARS_BWD) * esz
@@ -356,19 +380,21 @@ def run_ours(a):
             "config": {"workload": workload_name(a), "arz": {"lanes_per_gpu": B, "cells": N, "dx": 5.0, "dt": 0.01,
                                                              "u_max": 30.0},
                        "idm": {"vehicles_per_gpu": V, "lane_vehicles": a.lane_vehicles, "params": "per-vehicle"},
-                       "sim_steps": T, "ckpt_every": a.ckpt_every, "parallelism": "lane shards x%d, all-reduce(loss)" % world,
+                       "sim_steps": T, "ckpt_every": arz_K, "arz_lanes_per_chunk": arz_chunk,
+                       "arz_chunks_per_pass": len(arz_chunks), "idm_ckpt_every": a.idm_ckpt_every, "parallelism": "lane shards x%d, all-reduce(loss)" % world,
                        "l2": "inputs (%.1f GB per pass) are larger than the 126 MB L2" % ((2 * B * N + 8 * V) * esz / 1e9)},
             "idm": {"metric": "fwd+bwd vehicle-updates/s", "value": veh_updates / (idm_all / 1e3),
                     "unit": "vehicle-updates/s", "ms_per_step": idm_all / K},
             "phase_ms_per_step": {"arz_fwd": arz_fwd / K, "arz_bwd": arz_bwd / K, "arz_total": arz_all / K,
                                   "idm_fwd": idm_fwd / K, "idm_bwd": idm_bwd / K, "idm_total": idm_all / K},
-            "gpu_launches": 4 * K,
+            "gpu_launches": (2 * len(arz_chunks) + 2) * K,
             "roofline": {"kernel": "arz_rollout_bwd_kernel<%s>" % ("double" if a.dtype == "f64" else "float"),
                          "bound": "hbm", "achieved": bwd_bytes / bwd_s / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": bwd_bytes / bwd_s / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bwd_bytes,
-                         "note": "achieved = 6 scalars x cell-steps per launch / CUDA-event time of the backward "
-                                 "rollout; temporal fusion keeps real DRAM traffic far below this (see traffic)"},
+                         "launches_per_pass": len(arz_chunks),
+                         "note": "achieved = 6 scalars x cell-steps of one adjoint launch / its mean CUDA-event time; "
+                                 "traffic = measured DRAM bytes of that launch (ncu, scaled per cell-step)"},
             "roofline_fwd_bwd": {"arz": {"achieved": both_bytes / both_s / 1e9, "frac": both_bytes / both_s / 1e9 / peak,
                                          "bytes_per_update": (ARZ_SCALARS_FWD + ARZ_SCALARS_BWD) * esz},
                                  "idm": {"achieved": idm_bytes / idm_s / 1e9, "frac": idm_bytes / idm_s / 1e9 / peak,

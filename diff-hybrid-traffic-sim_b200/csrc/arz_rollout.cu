@@ -21,40 +21,30 @@
 // road/lane/dmacro_lane.py:68-132,234-310).
 #include <cstdint>
 #include <cstdlib>
-#include "dhts_arz.cuh"
+#include "dhts_arz_lean.cuh"
 #include "dhts_api.h"
 
 namespace dhts {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int RF_FWD = 6;    // r, y, us, uc, w, sq
-constexpr int RF_ADJ = 11;   // + rs, ri, uf, gr, gy
 
-template <typename T> struct LaneK { T umax, inv_umax, inv15, dx, cc; };
-
-template <typename T> __device__ __forceinline__ void pack_fwd(const Cell<T>& c, T* a) {
-    a[0] = c.r; a[1] = c.y; a[2] = c.us; a[3] = c.uc; a[4] = c.w; a[5] = c.sq;
+// 64-bit shuffles as two explicit 32-bit ones (keeps the register pairs in place)
+__device__ __forceinline__ double shfl_up1(double v) {
+    int lo = __shfl_up_sync(FULL, __double2loint(v), 1), hi = __shfl_up_sync(FULL, __double2hiint(v), 1);
+    return __hiloint2double(hi, lo);
 }
-template <typename T> __device__ __forceinline__ Cell<T> unpack_fwd(const T* a) {
-    Cell<T> c; c.r = a[0]; c.y = a[1]; c.us = a[2]; c.uc = a[3]; c.w = a[4]; c.sq = a[5];
-    c.rs = T(0); c.ri = T(0); c.uf = T(0);
-    return c;
+__device__ __forceinline__ float shfl_up1(float v) { return __shfl_up_sync(FULL, v, 1); }
+__device__ __forceinline__ double shfl_down1(double v) {
+    int lo = __shfl_down_sync(FULL, __double2loint(v), 1), hi = __shfl_down_sync(FULL, __double2hiint(v), 1);
+    return __hiloint2double(hi, lo);
 }
-template <typename T> __device__ __forceinline__ void pack_adj(const Cell<T>& c, T gr, T gy, T* a) {
-    a[0] = c.r; a[1] = c.y; a[2] = c.us; a[3] = c.uc; a[4] = c.w; a[5] = c.sq; a[6] = c.rs; a[7] = c.ri; a[8] = c.uf;
-    a[9] = gr; a[10] = gy;
-}
-template <typename T> __device__ __forceinline__ Cell<T> unpack_adj(const T* a) {
-    Cell<T> c; c.r = a[0]; c.y = a[1]; c.us = a[2]; c.uc = a[3]; c.w = a[4]; c.sq = a[5]; c.rs = a[6]; c.ri = a[7];
-    c.uf = a[8];
-    return c;
-}
+__device__ __forceinline__ float shfl_down1(float v) { return __shfl_down_sync(FULL, v, 1); }
 
 // value held by thread t-1 -> thread t (shuffle; warp edges through the mailbox). All threads must call.
 template <typename T, int NF>
 __device__ __forceinline__ void from_left(const T* mine, T* out, T* box, int warp, unsigned lane) {
 #pragma unroll
-    for (int f = 0; f < NF; f++) out[f] = __shfl_up_sync(FULL, mine[f], 1);
+    for (int f = 0; f < NF; f++) out[f] = shfl_up1(mine[f]);
     if (lane == 31) {
 #pragma unroll
         for (int f = 0; f < NF; f++) box[warp * NF + f] = mine[f];
@@ -69,7 +59,7 @@ __device__ __forceinline__ void from_left(const T* mine, T* out, T* box, int war
 template <typename T, int NF>
 __device__ __forceinline__ void from_right(const T* mine, T* out, T* box, int warp, int nwarp, unsigned lane) {
 #pragma unroll
-    for (int f = 0; f < NF; f++) out[f] = __shfl_down_sync(FULL, mine[f], 1);
+    for (int f = 0; f < NF; f++) out[f] = shfl_down1(mine[f]);
     if (lane == 0) {
 #pragma unroll
         for (int f = 0; f < NF; f++) box[warp * NF + f] = mine[f];
@@ -81,53 +71,67 @@ __device__ __forceinline__ void from_right(const T* mine, T* out, T* box, int wa
     }
 }
 
-template <typename T, int C> __device__ __forceinline__ void load_chunk(const T* __restrict__ p, T* v) {
-#pragma unroll
-    for (int c = 0; c < C; c++) v[c] = p[c];
-}
-template <> __device__ __forceinline__ void load_chunk<double, 4>(const double* __restrict__ p, double* v) {
-    if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+// Chunk loads / stores.  C > 1 is only planned when every row start is 16-byte aligned (plan_reg), so the
+// vector forms are unconditional.
+template <typename T, int C> struct Chunk;
+template <typename T> struct Chunk<T, 1> {
+    static __device__ __forceinline__ void ld(const T* __restrict__ p, T* v) { v[0] = p[0]; }
+    static __device__ __forceinline__ void st(T* __restrict__ p, const T* v) { p[0] = v[0]; }
+};
+template <> struct Chunk<double, 2> {
+    static __device__ __forceinline__ void ld(const double* __restrict__ p, double* v) {
+        double2 a = *reinterpret_cast<const double2*>(p); v[0] = a.x; v[1] = a.y;
+    }
+    static __device__ __forceinline__ void st(double* __restrict__ p, const double* v) {
+        *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+    }
+};
+template <> struct Chunk<double, 4> {
+    static __device__ __forceinline__ void ld(const double* __restrict__ p, double* v) {
         double2 a = reinterpret_cast<const double2*>(p)[0], b = reinterpret_cast<const double2*>(p)[1];
         v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
-    } else { v[0] = p[0]; v[1] = p[1]; v[2] = p[2]; v[3] = p[3]; }
-}
-template <> __device__ __forceinline__ void load_chunk<float, 4>(const float* __restrict__ p, float* v) {
-    if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
-        float4 a = reinterpret_cast<const float4*>(p)[0];
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-    } else { v[0] = p[0]; v[1] = p[1]; v[2] = p[2]; v[3] = p[3]; }
-}
-template <typename T, int C> __device__ __forceinline__ void store_chunk(T* __restrict__ p, const T* v) {
-#pragma unroll
-    for (int c = 0; c < C; c++) p[c] = v[c];
-}
-template <> __device__ __forceinline__ void store_chunk<double, 4>(double* __restrict__ p, const double* v) {
-    if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+    }
+    static __device__ __forceinline__ void st(double* __restrict__ p, const double* v) {
         reinterpret_cast<double2*>(p)[0] = make_double2(v[0], v[1]);
         reinterpret_cast<double2*>(p)[1] = make_double2(v[2], v[3]);
-    } else { p[0] = v[0]; p[1] = v[1]; p[2] = v[2]; p[3] = v[3]; }
-}
-template <> __device__ __forceinline__ void store_chunk<float, 4>(float* __restrict__ p, const float* v) {
-    if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
-    else { p[0] = v[0]; p[1] = v[1]; p[2] = v[2]; p[3] = v[3]; }
-}
+    }
+};
+template <> struct Chunk<float, 2> {
+    static __device__ __forceinline__ void ld(const float* __restrict__ p, float* v) {
+        float2 a = *reinterpret_cast<const float2*>(p); v[0] = a.x; v[1] = a.y;
+    }
+    static __device__ __forceinline__ void st(float* __restrict__ p, const float* v) {
+        *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+    }
+};
+template <> struct Chunk<float, 4> {
+    static __device__ __forceinline__ void ld(const float* __restrict__ p, float* v) {
+        float4 a = *reinterpret_cast<const float4*>(p); v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    }
+    static __device__ __forceinline__ void st(float* __restrict__ p, const float* v) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+template <typename T, int C> __device__ __forceinline__ void load_chunk(const T* __restrict__ p, T* v) { Chunk<T, C>::ld(p, v); }
+template <typename T, int C> __device__ __forceinline__ void store_chunk(T* __restrict__ p, const T* v) { Chunk<T, C>::st(p, v); }
 
 // Shared-memory layout of a CTA: per-lane constants, per-lane ghost records, two mailboxes x two parities.
+constexpr int GH_F = RF_FWD, GH_A = 10;
 template <typename T> struct Shm {
     LaneK<T>* lk;     // [lpc]
-    T* ghost;         // [lpc][2][9]   left / right ghost records (ADJ fields included)
-    T* gacc;          // [lpc][4]      ghost adjoints (r,y) x (left,right), adjoint kernel only
+    T* ghostF;        // [lpc][2][GH_F]   left / right ghost forward records
+    T* ghostA;        // [lpc][2][GH_A]   left / right ghost adjoint records
     T* boxL;          // [2][nwarp][RF_ADJ]
     T* boxR;          // [2][nwarp][4]
 };
 template <typename T> __host__ __device__ inline size_t shm_bytes(int lpc, int nwarp) {
-    return sizeof(LaneK<T>) * lpc + sizeof(T) * ((size_t)lpc * (18 + 4) + (size_t)2 * nwarp * (RF_ADJ + 4)) + 16;
+    return sizeof(LaneK<T>) * lpc + sizeof(T) * ((size_t)lpc * 2 * (GH_F + GH_A) + (size_t)2 * nwarp * (RF_ADJ + 4)) + 16;
 }
 template <typename T> __device__ __forceinline__ Shm<T> carve_shm(unsigned char* raw, int lpc, int nwarp) {
     Shm<T> s;
     s.lk = reinterpret_cast<LaneK<T>*>(raw);
     T* p = reinterpret_cast<T*>(raw + sizeof(LaneK<T>) * lpc);
-    s.ghost = p; p += lpc * 18; s.gacc = p; p += lpc * 4;
+    s.ghostF = p; p += lpc * 2 * GH_F; s.ghostA = p; p += lpc * 2 * GH_A;
     s.boxL = p; p += 2 * nwarp * RF_ADJ; s.boxR = p;
     return s;
 }
@@ -135,59 +139,76 @@ template <typename T> __device__ __forceinline__ Shm<T> carve_shm(unsigned char*
 template <typename T>
 __device__ __forceinline__ void setup_group(const Shm<T>& s, int lane0, int nl, const T* __restrict__ ghost,
                                             const T* __restrict__ dx, const T* __restrict__ umax_, T dt) {
-    for (int l = threadIdx.x; l < nl; l += blockDim.x) {
-        T um = umax_[lane0 + l], d = dx[lane0 + l];
-        LaneK<T> k; k.umax = um; k.inv_umax = T(1) / um; k.inv15 = T(1) / (T(1.5) * um); k.dx = d; k.cc = dt / d;
-        s.lk[l] = k;
-    }
+    for (int l = threadIdx.x; l < nl; l += blockDim.x) s.lk[l] = make_lanek<T>(umax_[lane0 + l], dx[lane0 + l], dt);
     for (int e = threadIdx.x; e < nl * 2; e += blockDim.x) {
         int l = e >> 1, side = e & 1;
-        const T* g = ghost + ((size_t)(lane0 + l) * 2 + side) * 3;
-        Cell<T> c = derive_cell_stored<T, true>(g[0], g[1], g[2], T(0), false, umax_[lane0 + l]);   // from_r_u record
-        T* o = s.ghost + (l * 2 + side) * 9;
-        o[0] = c.r; o[1] = c.y; o[2] = c.us; o[3] = c.uc; o[4] = c.w; o[5] = c.sq; o[6] = c.rs; o[7] = c.ri; o[8] = c.uf;
+        const T* g = ghost + ((size_t)(lane0 + l) * 2 + side) * 3;          // (r, y, u) built by from_r_u
+        const LaneK<T> k = make_lanek<T>(umax_[lane0 + l], dx[lane0 + l], dt);
+        FRec<T> f = fderive<T, true>(g[0], g[1], g[2], k);
+        if (g[0] < DHTS_EPS) f.w = w_vacuum(g[0], f.us, k);
+        pack(f, s.ghostF + (l * 2 + side) * GH_F);
+        ARec<T> a = aderive<T, true>(g[0], g[1], g[2], k);
+        if (g[0] < DHTS_EPS) fix_vacuum_adj(a, g[1], k);
+        T tmp[RF_ADJ];
+        pack(a, T(0), T(0), tmp);
+        for (int i = 0; i < GH_A; i++) s.ghostA[(l * 2 + side) * GH_A + i] = tmp[i];
     }
-    for (int e = threadIdx.x; e < nl * 4; e += blockDim.x) s.gacc[e] = T(0);
 }
 
-// One forward step of this thread's chunk (Godunov update, _macro_lane.py:83-114).
-// u_first != nullptr only for a step whose cells carry an explicitly stored speed (set_r_u, step 0).
-template <typename T, int C>
-__device__ __forceinline__ bool chunk_fwd_step(T* r, T* y, const T* u_first, bool active, bool first_chunk,
-                                               bool last_chunk, const LaneK<T>& k, const T* ghostL, const T* ghostR,
-                                               T dt, T* boxL, T* boxR, int warp, int nwarp, unsigned lane) {
-    Cell<T> rec[C];
-#pragma unroll
-    for (int c = 0; c < C; c++)
-        rec[c] = u_first ? derive_cell_stored<T, false>(r[c], y[c], u_first[c], T(0), false, k.umax)
-                         : derive_cell<T, false>(r[c], y[c], k.umax);
+// One forward step of this thread's chunk (Godunov update, _macro_lane.py:83-114), STREAMED: only the record
+// of the last cell is derived up front (the right neighbour needs it); the sweep then derives cell c, solves
+// the interface on its left and finishes the update of cell c-1, so that no per-cell array stays live.
+// STORED: the cells carry an explicitly stored speed (set_r_u, step 0).  CHECK: evaluate the CFL condition.
+template <typename T, bool STORED>
+__device__ __forceinline__ FRec<T> fcell(T r, T y, T us, const LaneK<T>& k) {
+    FRec<T> c = fderive<T, STORED>(r, y, us, k);
+    if (r < DHTS_EPS) c.w = w_vacuum(r, c.us, k);      // rare
+    return c;
+}
+
+template <typename T, int C, bool STORED, bool CHECK>
+__device__ __forceinline__ bool chunk_fwd_step(T* r, T* y, const T* us, bool first_chunk, bool last_chunk,
+                                               const LaneK<T>& k, const T* ghostL, const T* ghostR, T dt, T* boxL,
+                                               T* boxR, int warp, int nwarp, unsigned lane) {
+    const FRec<T> last = fcell<T, STORED>(r[C - 1], y[C - 1], STORED ? us[C - 1] : T(0), k);
     T mine[RF_FWD], left[RF_FWD];
-    pack_fwd(rec[C - 1], mine);
+    pack(last, mine);
     from_left<T, RF_FWD>(mine, left, boxL, warp, lane);
-    Cell<T> L = first_chunk ? unpack_adj(ghostL) : unpack_fwd(left);
-    T fr[C + 1], fy[C + 1];
+    FRec<T> L = first_chunk ? unpack_f(ghostL) : unpack_f(left);
+    bool okL = CHECK ? cell_speed_ok(L.us, L.w, k) : true;
     bool bad = false;
+    T f0[2], fpr = T(0), fpy = T(0);
 #pragma unroll
     for (int c = 0; c < C; c++) {
-        Riem<T> o = riemann(L, rec[c], k.umax, k.inv_umax, k.inv15, dt, k.dx);
-        fr[c] = o.r0 * o.u0; fy[c] = o.y0 * o.u0;
-        bad |= o.cfl_bad;
-        L = rec[c];
+        const FRec<T> cur = (c == C - 1) ? last : fcell<T, STORED>(r[c], y[c], STORED ? us[c] : T(0), k);
+        T fr, fy;
+        bool sus = false;
+        fflux(L, cur.r, cur.us, k, fr, fy, sus);
+        if (CHECK) {
+            const bool okR = cell_speed_ok(cur.us, cur.w, k);
+            if (sus || !okL || !okR) bad |= cfl_exact_bad(L.r, L.us, L.sq, L.w, cur.r, cur.us, k, dt);   // never in a valid run
+            okL = okR;
+        }
+        if (c == 0) { f0[0] = fr; f0[1] = fy; }
+        else {
+            r[c - 1] = fma(fpr - fr, k.cc, r[c - 1]);
+            y[c - 1] = fma(fpy - fy, k.cc, y[c - 1]);
+        }
+        fpr = fr; fpy = fy; L = cur;
     }
-    T f0[2] = {fr[0], fy[0]}, fR[2];
+    T fR[2];
     from_right<T, 2>(f0, fR, boxR, warp, nwarp, lane);
     if (last_chunk) {   // interface with the right ghost cell
-        Riem<T> o = riemann(L, unpack_adj(ghostR), k.umax, k.inv_umax, k.inv15, dt, k.dx);
-        fR[0] = o.r0 * o.u0; fR[1] = o.y0 * o.u0;
-        bad |= o.cfl_bad;
+        const FRec<T> G = unpack_f(ghostR);
+        bool sus = false;
+        fflux(L, G.r, G.us, k, fR[0], fR[1], sus);
+        if (CHECK) {
+            if (sus || !okL || !cell_speed_ok(G.us, G.w, k)) bad |= cfl_exact_bad(L.r, L.us, L.sq, L.w, G.r, G.us, k, dt);
+        }
     }
-    fr[C] = fR[0]; fy[C] = fR[1];
-#pragma unroll
-    for (int c = 0; c < C; c++) {
-        r[c] = r[c] + (fr[c] - fr[c + 1]) * k.cc;
-        y[c] = y[c] + (fy[c] - fy[c + 1]) * k.cc;
-    }
-    return bad && active;
+    r[C - 1] = fma(fpr - fR[0], k.cc, r[C - 1]);
+    y[C - 1] = fma(fpy - fR[1], k.cc, y[C - 1]);
+    return bad;
 }
 
 template <typename T, int C, int MB>
@@ -212,28 +233,91 @@ __global__ void __launch_bounds__(1024 / C, MB) arz_rollout_fwd_reg_kernel(const
         setup_group(s, lane0, nl, ghost, dx, umax_, dt);
         __syncthreads();
         const LaneK<T> k = s.lk[ll];
-        const T* gL = s.ghost + (ll * 2) * 9; const T* gR = gL + 9;
+        const T* gL = s.ghostF + (ll * 2) * GH_F; const T* gR = gL + GH_F;
         const size_t off = (size_t)(lane0 + ll) * N + (size_t)kc * C;
-        T r[C], y[C], us[C];
+        const bool first_chunk = kc == 0, last_chunk = kc == tpl - 1;
+        const size_t BN = (size_t)B * N;
+        T r[C], y[C];
         load_chunk<T, C>(r0 + off, r); load_chunk<T, C>(y0 + off, y);
-        if (u0) load_chunk<T, C>(u0 + off, us);
+        bool lbad = false;
+        T* blA = s.boxL; T* blB = s.boxL + nwarp * RF_ADJ;        // double-buffered mailboxes, swapped every step
+        T* brA = s.boxR; T* brB = s.boxR + nwarp * 4;
+        T* ck = ckpt ? ckpt + off : nullptr;                       // next checkpoint slot of this chunk
+        int next_ck = 0;
         for (int t = 0; t < steps; t++) {
-            if (ckpt && t % K == 0 && active) {
-                T* cr = ckpt + ((size_t)(t / K) * 2) * B * N + off;
-                store_chunk<T, C>(cr, r); store_chunk<T, C>(cr + (size_t)B * N, y);
+            if (ck && t == next_ck) {
+                if (active) { store_chunk<T, C>(ck, r); store_chunk<T, C>(ck + BN, y); }
+                ck += 2 * BN; next_ck += K;
             }
-            const int par = t & 1;
-            bad |= chunk_fwd_step<T, C>(r, y, (t == 0 && u0) ? us : nullptr, active, kc == 0, kc == tpl - 1, k, gL, gR,
-                                        dt, s.boxL + par * nwarp * RF_ADJ, s.boxR + par * nwarp * 4, warp, nwarp, lane);
+            if (t == 0 && u0) {
+                T us[C];
+                load_chunk<T, C>(u0 + off, us);
+                lbad |= chunk_fwd_step<T, C, true, true>(r, y, us, first_chunk, last_chunk, k, gL, gR, dt, blA, brA, warp, nwarp, lane);
+            } else
+                lbad |= chunk_fwd_step<T, C, false, true>(r, y, nullptr, first_chunk, last_chunk, k, gL, gR, dt, blA, brA, warp, nwarp, lane);
+            T* x = blA; blA = blB; blB = x; x = brA; brA = brB; brB = x;
         }
+        bad |= lbad && active;
         if (active) {
             T u[C];
 #pragma unroll
-            for (int c = 0; c < C; c++) u[c] = (steps == 0 && u0) ? us[c] : compute_u(r[c], y[c], k.umax);
+            for (int c = 0; c < C; c++) u[c] = (steps == 0 && u0) ? u0[off + c] : compute_u(r[c], y[c], k.umax);
             store_chunk<T, C>(rT + off, r); store_chunk<T, C>(yT + off, y); store_chunk<T, C>(uT + off, u);
         }
     }
     if (bad) atomicOr(flags, FLAG_CFL);
+}
+
+// One adjoint step of this thread's chunk: (gr, gy) <- VJP of the step taken from state (r, y)
+// (flux-difference form of dmacro_lane.py:293-303), streamed like the forward step: interface c
+// gives A^T w to cell c-1 and B^T w to cell c, so cell c-1 is finished as soon as interface c is done.
+// accL / accR collect the ghost adjoints.
+template <typename T, bool STORED>
+__device__ __forceinline__ ARec<T> acell(T r, T y, T us, const LaneK<T>& k) {
+    ARec<T> c = aderive<T, STORED>(r, y, us, k);
+    if (r < DHTS_EPS) fix_vacuum_adj(c, y, k);         // rare
+    return c;
+}
+
+template <typename T, int C, bool STORED>
+__device__ __forceinline__ bool chunk_adj_step(const T* r, const T* y, const T* us, T* gr, T* gy, bool first_chunk,
+                                               bool last_chunk, const LaneK<T>& k, const T* ghostL, const T* ghostR,
+                                               T* accL, T* accR, T* boxL, T* boxR, int warp, int nwarp, unsigned lane) {
+    const ARec<T> last = acell<T, STORED>(r[C - 1], y[C - 1], STORED ? us[C - 1] : T(0), k);
+    T mine[RF_ADJ], left[RF_ADJ];
+    pack(last, gr[C - 1], gy[C - 1], mine);
+    from_left<T, RF_ADJ>(mine, left, boxL, warp, lane);
+    ARec<T> L = first_chunk ? unpack_a(ghostL) : unpack_a(left);
+    T gLr = first_chunk ? T(0) : left[10], gLy = first_chunk ? T(0) : left[11];   // OLD adjoint of the cell on the left
+    T a0[2], bpr = T(0), bpy = T(0);
+    bool nan = false;
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        const ARec<T> cur = (c == C - 1) ? last : acell<T, STORED>(r[c], y[c], STORED ? us[c] : T(0), k);
+        const T gcr = gr[c], gcy = gy[c];
+        T ar, ay, br, by;
+        aflux(L, cur, gcr - gLr, gcy - gLy, k, ar, ay, br, by);
+        if (c == 0) { a0[0] = ar; a0[1] = ay; }
+        else {
+            gr[c - 1] = fma(k.cc, ar + bpr, gLr);
+            gy[c - 1] = fma(k.cc, ay + bpy, gLy);
+            nan |= t_isnan(gr[c - 1]) || t_isnan(gy[c - 1]);
+        }
+        bpr = br; bpy = by; L = cur; gLr = gcr; gLy = gcy;
+    }
+    T aR[2];
+    from_right<T, 2>(a0, aR, boxR, warp, nwarp, lane);
+    if (last_chunk) {   // interface with the right ghost (its updated-state adjoint is zero)
+        const ARec<T> G = unpack_a(ghostR);
+        T pbr, pby;
+        aflux(L, G, -gLr, -gLy, k, aR[0], aR[1], pbr, pby);
+        accR[0] = fma(k.cc, pbr, accR[0]); accR[1] = fma(k.cc, pby, accR[1]);
+    }
+    if (first_chunk) { accL[0] = fma(k.cc, a0[0], accL[0]); accL[1] = fma(k.cc, a0[1], accL[1]); }
+    gr[C - 1] = fma(k.cc, aR[0] + bpr, gLr);
+    gy[C - 1] = fma(k.cc, aR[1] + bpy, gLy);
+    nan |= t_isnan(gr[C - 1]) || t_isnan(gy[C - 1]);
+    return nan;
 }
 
 template <typename T, int C, int MB>
@@ -254,6 +338,7 @@ __global__ void __launch_bounds__(1024 / C, MB) arz_rollout_bwd_reg_kernel(const
     const int ngroup = (B + lpc - 1) / lpc;
     const int S = (steps + K - 1) / K;
     const size_t sstride = (size_t)2 * lpc * N;               // one stashed state of the group
+    const size_t BN = (size_t)B * N;
     T* scr = scratch + (size_t)blockIdx.x * K * sstride;
     bool bad = false;
     for (int grp = blockIdx.x; grp < ngroup; grp += gridDim.x) {
@@ -265,11 +350,13 @@ __global__ void __launch_bounds__(1024 / C, MB) arz_rollout_bwd_reg_kernel(const
         setup_group(s, lane0, nl, ghost, dx, umax_, dt);
         __syncthreads();
         const LaneK<T> k = s.lk[ll];
-        const T* gL = s.ghost + (ll * 2) * 9; const T* gR = gL + 9;
+        const T* gLf = s.ghostF + (ll * 2) * GH_F; const T* gRf = gLf + GH_F;
+        const T* gLa = s.ghostA + (ll * 2) * GH_A; const T* gRa = gLa + GH_A;
         const size_t off = (size_t)(lane0 + ll) * N + (size_t)kc * C;
         const size_t soff = (size_t)ll * N + (size_t)kc * C;
-        T gr[C], gy[C], us[C];
+        T gr[C], gy[C];
         T accL[2] = {T(0), T(0)}, accR[2] = {T(0), T(0)};     // ghost adjoints of this lane (first / last chunk)
+        bool nan = false;
         // terminal adjoint; uT = compute_u(rT, yT) is produced inside the operator
 #pragma unroll
         for (int c = 0; c < C; c++) {
@@ -279,72 +366,65 @@ __global__ void __launch_bounds__(1024 / C, MB) arz_rollout_bwd_reg_kernel(const
                 T gu = g_uT[off + c]; gr[c] += gu * dr; gy[c] += gu * dy;
             }
         }
-        if (u0) load_chunk<T, C>(u0 + off, us);
-        for (int seg = S - 1; seg >= 0; seg--) {
-            const int t0 = seg * K, ks = min(K, steps - t0);
-            T r[C], y[C];
-            {
-                const T* cr = ckpt + ((size_t)seg * 2) * B * N + off;
-                load_chunk<T, C>(cr, r); load_chunk<T, C>(cr + (size_t)B * N, y);
+        T* blA = s.boxL; T* blB = s.boxL + nwarp * RF_ADJ;
+        T* brA = s.boxR; T* brB = s.boxR + nwarp * 4;
+#define DHTS_SWAP_BOXES { T* x_ = blA; blA = blB; blB = x_; x_ = brA; brA = brB; brB = x_; }
+        if (K == 1) {
+            // every state was stored by the forward pass: stream them back, one step ahead of the arithmetic
+            T r[C], y[C], rn[C], yn[C];
+            if (steps > 0) {
+                const T* c0 = ckpt + (size_t)(steps - 1) * 2 * BN + off;
+                load_chunk<T, C>(c0, r); load_chunk<T, C>(c0 + BN, y);
             }
-            // recompute the segment, stashing every state (the stash stays in L2)
-            for (int kk = 0; kk < ks; kk++) {
-                T* sr = scr + (size_t)kk * sstride + soff;
-                if (active) { store_chunk<T, C>(sr, r); store_chunk<T, C>(sr + (size_t)lpc * N, y); }
-                if (kk + 1 < ks) {
-                    const int par = kk & 1;
-                    chunk_fwd_step<T, C>(r, y, (t0 + kk == 0 && u0) ? us : nullptr, active, first_chunk, last_chunk, k,
-                                         gL, gR, dt, s.boxL + par * nwarp * RF_ADJ, s.boxR + par * nwarp * 4, warp,
-                                         nwarp, lane);
+            const T* cr = ckpt + (size_t)(steps > 0 ? steps - 1 : 0) * 2 * BN + off;
+            for (int t = steps - 1; t >= 0; t--) {
+                if (t > 0) {
+                    cr -= 2 * BN;
+                    load_chunk<T, C>(cr, rn); load_chunk<T, C>(cr + BN, yn);
                 }
+                if (t == 0 && u0)
+                    { T us_[C]; load_chunk<T, C>(u0 + off, us_); nan |= chunk_adj_step<T, C, true>(r, y, us_, gr, gy, first_chunk, last_chunk, k, gLa, gRa, accL, accR, blA, brA, warp, nwarp, lane); }
+                else
+                    nan |= chunk_adj_step<T, C, false>(r, y, nullptr, gr, gy, first_chunk, last_chunk, k, gLa, gRa, accL, accR, blA, brA, warp, nwarp, lane);
+                DHTS_SWAP_BOXES
+#pragma unroll
+                for (int c = 0; c < C; c++) { r[c] = rn[c]; y[c] = yn[c]; }
             }
-            // adjoint steps, last to first
-            for (int kk = ks - 1; kk >= 0; kk--) {
-                const int par = kk & 1;
-                T* boxL = s.boxL + par * nwarp * RF_ADJ; T* boxR = s.boxR + par * nwarp * 4;
-                if (kk != ks - 1) {
-                    const T* sr = scr + (size_t)kk * sstride + soff;
-                    load_chunk<T, C>(sr, r); load_chunk<T, C>(sr + (size_t)lpc * N, y);
+        } else {
+            for (int seg = S - 1; seg >= 0; seg--) {
+                const int t0 = seg * K, ks = min(K, steps - t0);
+                T r[C], y[C];
+                {
+                    const T* cr = ckpt + ((size_t)seg * 2) * BN + off;
+                    load_chunk<T, C>(cr, r); load_chunk<T, C>(cr + BN, y);
                 }
-                const bool stored = (t0 + kk == 0 && u0);
-                Cell<T> rec[C];
-#pragma unroll
-                for (int c = 0; c < C; c++)
-                    rec[c] = stored ? derive_cell_stored<T, true>(r[c], y[c], us[c], T(0), false, k.umax)
-                                    : derive_cell<T, true>(r[c], y[c], k.umax);
-                T mine[RF_ADJ], left[RF_ADJ];
-                pack_adj(rec[C - 1], gr[C - 1], gy[C - 1], mine);
-                from_left<T, RF_ADJ>(mine, left, boxL, warp, lane);
-                Cell<T> L = first_chunk ? unpack_adj(gL) : unpack_adj(left);
-                T gLr = first_chunk ? T(0) : left[9], gLy = first_chunk ? T(0) : left[10];
-                // sweep my C left-interfaces: pa -> cell on the left, pb -> my cell
-                T ar[C + 1], ay[C + 1], br[C], by[C];
-#pragma unroll
-                for (int c = 0; c < C; c++) {
-                    Riem<T> o = riemann(L, rec[c], k.umax, k.inv_umax, k.inv15, dt, k.dx);
-                    riemann_adj(L, rec[c], o, k.umax, k.inv_umax, k.inv15, gr[c] - gLr, gy[c] - gLy, ar[c], ay[c],
-                                br[c], by[c]);
-                    L = rec[c]; gLr = gr[c]; gLy = gy[c];
+                // recompute the segment, stashing every state (the stash stays in L2)
+                for (int kk = 0; kk < ks; kk++) {
+                    T* sr = scr + (size_t)kk * sstride + soff;
+                    if (active) { store_chunk<T, C>(sr, r); store_chunk<T, C>(sr + (size_t)lpc * N, y); }
+                    if (kk + 1 < ks) {
+                        if (t0 + kk == 0 && u0)
+                            { T us_[C]; load_chunk<T, C>(u0 + off, us_); chunk_fwd_step<T, C, true, false>(r, y, us_, first_chunk, last_chunk, k, gLf, gRf, dt, blA, brA, warp, nwarp, lane); }
+                        else
+                            chunk_fwd_step<T, C, false, false>(r, y, nullptr, first_chunk, last_chunk, k, gLf, gRf, dt, blA, brA, warp, nwarp, lane);
+                        DHTS_SWAP_BOXES
+                    }
                 }
-                T a0[2] = {ar[0], ay[0]}, aR[2];
-                from_right<T, 2>(a0, aR, boxR, warp, nwarp, lane);
-                if (last_chunk) {   // interface with the right ghost (its updated-state adjoint is zero)
-                    Cell<T> G = unpack_adj(gR);
-                    Riem<T> o = riemann(L, G, k.umax, k.inv_umax, k.inv15, dt, k.dx);
-                    T pbr, pby;
-                    riemann_adj(L, G, o, k.umax, k.inv_umax, k.inv15, -gLr, -gLy, aR[0], aR[1], pbr, pby);
-                    accR[0] += k.cc * pbr; accR[1] += k.cc * pby;
-                }
-                if (first_chunk) { accL[0] += k.cc * ar[0]; accL[1] += k.cc * ay[0]; }
-                ar[C] = aR[0]; ay[C] = aR[1];
-#pragma unroll
-                for (int c = 0; c < C; c++) {
-                    gr[c] = gr[c] + k.cc * (ar[c + 1] + br[c]);
-                    gy[c] = gy[c] + k.cc * (ay[c + 1] + by[c]);
-                    bad |= active && (t_isnan(gr[c]) || t_isnan(gy[c]));
+                // adjoint steps, last to first
+                for (int kk = ks - 1; kk >= 0; kk--) {
+                    if (kk != ks - 1) {
+                        const T* sr = scr + (size_t)kk * sstride + soff;
+                        load_chunk<T, C>(sr, r); load_chunk<T, C>(sr + (size_t)lpc * N, y);
+                    }
+                    if (t0 + kk == 0 && u0)
+                        { T us_[C]; load_chunk<T, C>(u0 + off, us_); nan |= chunk_adj_step<T, C, true>(r, y, us_, gr, gy, first_chunk, last_chunk, k, gLa, gRa, accL, accR, blA, brA, warp, nwarp, lane); }
+                    else
+                        nan |= chunk_adj_step<T, C, false>(r, y, nullptr, gr, gy, first_chunk, last_chunk, k, gLa, gRa, accL, accR, blA, brA, warp, nwarp, lane);
+                    DHTS_SWAP_BOXES
                 }
             }
         }
+        bad |= nan && active;
         if (active) {
             store_chunk<T, C>(g_r0 + off, gr); store_chunk<T, C>(g_y0 + off, gy);
             if (g_ghost) {
@@ -362,6 +442,8 @@ __global__ void __launch_bounds__(1024 / C, MB) arz_rollout_bwd_reg_kernel(const
 struct RegPlan { int C, lpc, threads, grid, mb; size_t smem; };
 
 static int round32(int x) { return (x + 31) / 32 * 32; }
+// vector chunk loads need 16-byte aligned bases (row offsets are multiples of C elements by construction)
+static bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 static int sm_count_r() {
     static int n = 0;
@@ -373,11 +455,14 @@ static int sm_count_r() {
     return n;
 }
 
-// Measured on B200 (profiles/r1c): forward is fastest with 4 cells per thread capped at 128 registers
-// (2 CTAs of 256 threads per SM); the adjoint holds more live state and is fastest with 2 cells per thread.
+// Measured on B200 (profiles/r1e sweep, fp64, 8192 lanes x 1024 cells): both kernels are fastest with 4 cells per
+// thread capped at 128 registers (2 CTAs of 256 threads per SM) -- forward 57 ms vs 69-89 ms for the other
+// shapes, adjoint 97 ms (every state stored) / 149 ms (K = 32) vs 106-226 ms.
 template <typename T> static int plan_reg(int B, int N, bool adj, RegPlan* p) {
-    int want = adj ? 2 : 4;
-    if (const char* e = getenv("DHTS_ARZ_C")) {      // tuning knob: cells per thread (must divide N)
+    int want = 4;
+    const char* e = getenv(adj ? "DHTS_ARZ_C_BWD" : "DHTS_ARZ_C_FWD");     // tuning knob: cells per thread
+    if (!e) e = getenv("DHTS_ARZ_C");
+    if (e) {
         int c = atoi(e);
         if (c == 1 || c == 2 || c == 4) want = c;
     }
@@ -392,8 +477,10 @@ template <typename T> static int plan_reg(int B, int N, bool adj, RegPlan* p) {
     p->C = C; p->lpc = lpc; p->threads = round32(lpc * tpl);
     p->smem = shm_bytes<T>(lpc, p->threads / 32);
     p->grid = (B + lpc - 1) / lpc;
-    p->mb = adj ? 1 : 2;
-    if (const char* e = getenv("DHTS_ARZ_MB")) p->mb = atoi(e) == 2 ? 2 : 1;
+    p->mb = 2;
+    const char* m = getenv(adj ? "DHTS_ARZ_MB_BWD" : "DHTS_ARZ_MB_FWD");    // tuning knob: min CTAs per SM
+    if (!m) m = getenv("DHTS_ARZ_MB");
+    if (m) p->mb = atoi(m) == 2 ? 2 : 1;
     return DHTS_OK;
 }
 
@@ -416,6 +503,8 @@ static int rollout_fwd(const T* r0, const T* y0, const T* u0, const T* ghost, co
     RegPlan p;
     int rc = plan_reg<T>(B, N, false, &p);
     if (rc) return rc;
+    if (p.C > 1 && !(al16(r0) && al16(y0) && al16(u0) && al16(ckpt) && al16(rT) && al16(yT) && al16(uT)))
+        return DHTS_ERR_UNSUPPORTED;          // callers step with the tiled kernels instead
     if (K < 1) K = 1;
     int grid = p.grid;
 #define CALL(CC, MB) arz_rollout_fwd_reg_kernel<T, CC, MB><<<grid, p.threads, p.smem, st>>>(r0, y0, u0, ghost, dx, umax, dt, B, N, steps, K, p.lpc, ckpt, rT, yT, uT, flags);
@@ -438,6 +527,7 @@ template <typename T> static long long rollout_scratch_elems(int B, int N, int K
     RegPlan p;
     if (B <= 0) return 0;
     if (K < 1 || plan_reg<T>(B, N, true, &p)) return -1;
+    if (K == 1) return 0;                      // every state comes from the forward pass: nothing to stash
     return (long long)bwd_grid_r<T>(p) * K * 2 * p.lpc * N;
 }
 
@@ -446,15 +536,16 @@ static int rollout_bwd(const T* ckpt, const T* u0, const T* ghost, const T* dx, 
                        int steps, int K, const T* rT, const T* yT, const T* g_rT, const T* g_yT, const T* g_uT,
                        T* scratch, long long scratch_elems, T* g_r0, T* g_y0, T* g_ghost, int* flags,
                        cudaStream_t st) {
-    if (!ckpt || !ghost || !dx || !umax || !g_r0 || !g_y0 || !flags || !scratch || B < 0 || N < 1 || steps < 0 || K < 1)
+    if (!ckpt || !ghost || !dx || !umax || !g_r0 || !g_y0 || !flags || (!scratch && K > 1) || B < 0 || N < 1 || steps < 0 || K < 1)
         return DHTS_ERR_INVALID;
     if (g_uT && (!rT || !yT)) return DHTS_ERR_INVALID;
     if (B == 0) return DHTS_OK;
     RegPlan p;
     int rc = plan_reg<T>(B, N, true, &p);
     if (rc) return rc;
+    if (p.C > 1 && !(al16(ckpt) && al16(u0) && al16(scratch) && al16(g_r0) && al16(g_y0))) return DHTS_ERR_UNSUPPORTED;
     int grid = bwd_grid_r<T>(p);
-    if ((long long)grid * K * 2 * p.lpc * N > scratch_elems) return DHTS_ERR_INVALID;
+    if (K > 1 && (long long)grid * K * 2 * p.lpc * N > scratch_elems) return DHTS_ERR_INVALID;
 #define CALL(CC, MB) arz_rollout_bwd_reg_kernel<T, CC, MB><<<grid, p.threads, p.smem, st>>>(ckpt, u0, ghost, dx, umax, dt, B, N, steps, K, p.lpc, rT, yT, g_rT, g_yT, g_uT, scratch, g_r0, g_y0, g_ghost, flags);
     DHTS_C_DISPATCH(p, CALL)
 #undef CALL

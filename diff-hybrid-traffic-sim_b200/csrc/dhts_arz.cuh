@@ -27,7 +27,9 @@ constexpr int FLAG_COLLISION = 4;  // _micro_lane.py:151-162 print-and-continue
 template <typename T> __device__ __forceinline__ T t_sqrt(T x);
 template <> __device__ __forceinline__ double t_sqrt<double>(double x) { return sqrt(x); }
 template <> __device__ __forceinline__ float t_sqrt<float>(float x) { return sqrtf(x); }
-template <typename T> __device__ __forceinline__ T t_abs(T x) { return x < T(0) ? -x : x; }
+// fabs folds into the |x| operand modifier of the consuming instruction (a compare-and-select does not)
+__device__ __forceinline__ double t_abs(double x) { return fabs(x); }
+__device__ __forceinline__ float t_abs(float x) { return fabsf(x); }
 
 // Branch-free 1/sqrt(x) and 1/x for well-scaled positive x (densities, gaps): hardware
 // approximation (MUFU.RSQ64H / MUFU.RCP64H, ~2^-22) refined by one cubic step to ~1 ulp.  The library

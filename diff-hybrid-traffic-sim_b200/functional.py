@@ -39,11 +39,13 @@ def arz_step(r_pad, y_pad, u_pad, dx, umax, dt, flags, ueq_pad=None, want_case=F
                            flags.t, want_case)
 
 
-def arz_rollout(r0, u0, ghost_r, ghost_u, dx, umax, dt, steps, ckpt_every=32, flags=None):
+def arz_rollout(r0, u0, ghost_r, ghost_u, dx, umax, dt, steps, ckpt_every=32, flags=None, ckpt_buffer=None):
     """`steps` x RoadNetwork.forward over B disconnected dMacroLanes with static ghost cells, i.e. the
     loop of example/inverse/_inverse.py:91-99 for example/inverse/macro.py, batched:
     set_state_vector_u(r0, u0) -> steps x (boundary, forward, update_state) -> get_state_vector().
-    r0, u0 [B, N]; ghost_r, ghost_u [B, 2] (left, right).  Returns (rT, yT, uT) [B, N]."""
+    r0, u0 [B, N]; ghost_r, ghost_u [B, 2] (left, right).  Returns (rT, yT, uT) [B, N].
+    ckpt_buffer: optional flat tensor the state checkpoints are written into instead of a fresh allocation;
+    it must stay untouched until this rollout's backward has run (see arz_rollout_plan)."""
     B, N = r0.shape
     flags = flags or _lib.Flags(r0.device)
     dxl = _per_lane(dx, B, r0); uml = _per_lane(umax, B, r0)
@@ -51,7 +53,7 @@ def arz_rollout(r0, u0, ghost_r, ghost_u, dx, umax, dt, steps, ckpt_every=32, fl
     y0 = compute_y(r0, u0, um)                       # set_r_u, _arz.py:82-86 (autograd, true derivative)
     ghost = torch.stack([ghost_r, compute_y(ghost_r, ghost_u, um), ghost_u.detach()], dim=-1)   # from_r_u, :74-80
     try:
-        return ArzRolloutFn.apply(r0, y0, u0.detach(), ghost, dxl, uml, dt, steps, ckpt_every, flags.t)
+        return ArzRolloutFn.apply(r0, y0, u0.detach(), ghost, dxl, uml, dt, steps, ckpt_every, flags.t, ckpt_buffer)
     except _lib.UnsupportedShape:
         pass
     # lane too long for the smem-resident kernel: chain the tiled per-step kernels (still CUDA)
@@ -63,6 +65,26 @@ def arz_rollout(r0, u0, ghost_r, ghost_u, dx, umax, dt, steps, ckpt_every=32, fl
         u_pad = torch.cat([g[:, 0:1, 2], u.detach(), g[:, 1:2, 2]], dim=1)
         r, y, u = ArzStepFn.apply(r_pad, y_pad, u_pad, None, dxl, uml, dt, flags.t, False)
     return r, y, u
+
+
+def arz_rollout_plan(B, N, steps, dtype, device, mem_fraction=0.6, min_lanes=296):
+    """How to run a differentiable rollout of B lanes within the device's free memory: returns
+    (lanes_per_chunk, ckpt_every).  Storing EVERY state (ckpt_every = 1) removes the segment recompute from
+    the adjoint -- the fastest mode, 2 * N * steps scalars per lane -- so lanes are processed in chunks
+    that fit `mem_fraction` of the free HBM (180 GB on B200: ~6500 lanes of 1024 cells x 1000 steps in
+    fp64).  When not even `min_lanes` (two CTAs per SM) fit, fall back to sparse checkpoints + recompute."""
+    esz = torch.empty((), dtype=dtype).element_size()
+    free, _ = torch.cuda.mem_get_info(device)
+    per_lane = 2 * N * max(int(steps), 1) * esz
+    fit = int(free * mem_fraction) // per_lane
+    if fit >= min(B, min_lanes):
+        nchunk = -(-B // min(B, fit))                      # equal chunks (the last one may be a few lanes short)
+        chunk = -(-B // nchunk)
+        chunk += (-chunk) % 8
+        return min(chunk, B), 1
+    K = 32
+    per_lane = 2 * N * ((int(steps) + K - 1) // K) * esz
+    return max(1, min(B, int(free * mem_fraction) // per_lane)), K
 
 
 def idm_step(p, v, params, lane_off, head, dt, flags, veh_lane=None, want_flags=False):

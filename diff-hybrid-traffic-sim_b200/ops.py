@@ -85,14 +85,22 @@ class ArzRolloutFn(torch.autograd.Function):
     """(r0, y0)[B,N], ghost[B,2,3] -> (rT, yT, uT)[B,N] after `steps` fused steps with static ghosts."""
 
     @staticmethod
-    def forward(ctx, r0, y0, u0, ghost, dx, umax, dt, steps, ckpt_every, flags):
+    def forward(ctx, r0, y0, u0, ghost, dx, umax, dt, steps, ckpt_every, flags, ckpt_buffer=None):
         dev = _lib.require_cuda(r0, y0, u0, ghost, dx, umax, flags)
         r0, y0, u0, ghost, dx, umax = map(_c, (r0, y0, u0, ghost, dx, umax))
         B, N = r0.shape
         dt_, steps, K = float(dt), int(steps), max(1, int(ckpt_every))
         need_grad = any(ctx.needs_input_grad[i] for i in (0, 1, 3))
         S = (steps + K - 1) // K
-        ckpt = torch.empty((S, 2, B, N), dtype=r0.dtype, device=dev) if need_grad else None
+        ckpt = None
+        if need_grad:
+            n = S * 2 * B * N
+            if ckpt_buffer is not None:      # caller-owned arena, reused across sequential rollouts (lane chunks)
+                if ckpt_buffer.dtype != r0.dtype or ckpt_buffer.device != dev or ckpt_buffer.numel() < n:
+                    raise ValueError("ckpt_buffer must be a %s tensor on %s with >= %d elements" % (r0.dtype, dev, n))
+                ckpt = ckpt_buffer.view(-1)[:n].view(S, 2, B, N)
+            else:
+                ckpt = torch.empty((S, 2, B, N), dtype=r0.dtype, device=dev)
         rT = torch.empty_like(r0); yT = torch.empty_like(r0); uT = torch.empty_like(r0)
         with torch.cuda.device(dev):
             check(_fn("arz_rollout_fwd", r0.dtype)(ptr(r0), ptr(y0), ptr(u0), ptr(ghost), ptr(dx), ptr(umax),
@@ -125,7 +133,7 @@ class ArzRolloutFn(torch.autograd.Function):
                                                 ptr(g_gh), ptr(flags), stream_ptr(dev)), "dhts_arz_rollout_bwd")
         g_ghost = torch.zeros((B, 2, 3), dtype=dtype, device=dev)
         g_ghost[:, :, :2] = g_gh          # ghost u is a value-only input
-        return g_r0, g_y0, None, g_ghost, None, None, None, None, None, None
+        return g_r0, g_y0, None, g_ghost, None, None, None, None, None, None, None
 
 
 def csr_expand(lane_off: torch.Tensor, V: int) -> torch.Tensor:

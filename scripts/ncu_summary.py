@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--work", default=""); ap.add_argument("--command", default="")
     ap.add_argument("--cell-steps", type=float, default=0.0, help="cell-steps (or vehicle-steps) per ARZ launch")
     ap.add_argument("--traffic", action="store_true")
+    ap.add_argument("--suffix", default="", help="appended to the traffic.json keys, e.g. _k1 for the store-every-state mode")
     a = ap.parse_args()
     rows = list(csv.reader(open(a.raw_csv)))
     hdr, units = rows[0], rows[1]
@@ -57,7 +58,7 @@ def main():
             name = re.match(r"void (\w+)<(\w+)", k["Kernel Name"])
             if not name:
                 continue
-            key = name.group(1).replace("_reg_kernel", "").replace("_kernel", "") + ("_f64" if name.group(2) == "double" else "_f32")
+            key = name.group(1).replace("_reg_kernel", "").replace("_kernel", "") + ("_f64" if name.group(2) == "double" else "_f32") + a.suffix
             t[key] = {"dram_bytes_per_launch": k["dram__bytes_read.sum"] + k["dram__bytes_write.sum"], "work": a.work,
                       "source": os.path.basename(a.out_json)}
             if a.cell_steps and "arz" in key:
