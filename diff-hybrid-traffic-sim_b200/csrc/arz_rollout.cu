@@ -96,6 +96,14 @@ template <> struct Chunk<double, 4> {
         reinterpret_cast<double2*>(p)[1] = make_double2(v[2], v[3]);
     }
 };
+template <> struct Chunk<double, 8> {
+    static __device__ __forceinline__ void ld(const double* __restrict__ p, double* v) {
+        Chunk<double, 4>::ld(p, v); Chunk<double, 4>::ld(p + 4, v + 4);
+    }
+    static __device__ __forceinline__ void st(double* __restrict__ p, const double* v) {
+        Chunk<double, 4>::st(p, v); Chunk<double, 4>::st(p + 4, v + 4);
+    }
+};
 template <> struct Chunk<float, 2> {
     static __device__ __forceinline__ void ld(const float* __restrict__ p, float* v) {
         float2 a = *reinterpret_cast<const float2*>(p); v[0] = a.x; v[1] = a.y;
@@ -110,6 +118,14 @@ template <> struct Chunk<float, 4> {
     }
     static __device__ __forceinline__ void st(float* __restrict__ p, const float* v) {
         *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+template <> struct Chunk<float, 8> {
+    static __device__ __forceinline__ void ld(const float* __restrict__ p, float* v) {
+        Chunk<float, 4>::ld(p, v); Chunk<float, 4>::ld(p + 4, v + 4);
+    }
+    static __device__ __forceinline__ void st(float* __restrict__ p, const float* v) {
+        Chunk<float, 4>::st(p, v); Chunk<float, 4>::st(p + 4, v + 4);
     }
 };
 template <typename T, int C> __device__ __forceinline__ void load_chunk(const T* __restrict__ p, T* v) { Chunk<T, C>::ld(p, v); }
@@ -212,7 +228,7 @@ __device__ __forceinline__ bool chunk_fwd_step(T* r, T* y, const T* us, bool fir
 }
 
 template <typename T, int C, int MB>
-__global__ void __launch_bounds__(1024 / C, MB) arz_rollout_fwd_reg_kernel(const T* __restrict__ r0, const T* __restrict__ y0,
+__global__ void __launch_bounds__(1024 / C, (C == 8 ? 2 : 1) * MB) arz_rollout_fwd_reg_kernel(const T* __restrict__ r0, const T* __restrict__ y0,
                                            const T* __restrict__ u0, const T* __restrict__ ghost,
                                            const T* __restrict__ dx, const T* __restrict__ umax_, T dt, int B, int N,
                                            int steps, int K, int lpc, T* __restrict__ ckpt, T* __restrict__ rT,
@@ -321,7 +337,7 @@ __device__ __forceinline__ bool chunk_adj_step(const T* r, const T* y, const T* 
 }
 
 template <typename T, int C, int MB>
-__global__ void __launch_bounds__(1024 / C, MB) arz_rollout_bwd_reg_kernel(const T* __restrict__ ckpt, const T* __restrict__ u0,
+__global__ void __launch_bounds__(1024 / C, (C == 8 ? 2 : 1) * MB) arz_rollout_bwd_reg_kernel(const T* __restrict__ ckpt, const T* __restrict__ u0,
                                            const T* __restrict__ ghost, const T* __restrict__ dx,
                                            const T* __restrict__ umax_, T dt, int B, int N, int steps, int K, int lpc,
                                            const T* __restrict__ rT, const T* __restrict__ yT,
@@ -371,12 +387,10 @@ __global__ void __launch_bounds__(1024 / C, MB) arz_rollout_bwd_reg_kernel(const
 #define DHTS_SWAP_BOXES { T* x_ = blA; blA = blB; blB = x_; x_ = brA; brA = brB; brB = x_; }
         if (K == 1) {
             // every state was stored by the forward pass: stream them back, one step ahead of the arithmetic
+            // (measured: prefetching only into L2 and loading at the top of the step is 15 % slower)
             T r[C], y[C], rn[C], yn[C];
-            if (steps > 0) {
-                const T* c0 = ckpt + (size_t)(steps - 1) * 2 * BN + off;
-                load_chunk<T, C>(c0, r); load_chunk<T, C>(c0 + BN, y);
-            }
             const T* cr = ckpt + (size_t)(steps > 0 ? steps - 1 : 0) * 2 * BN + off;
+            if (steps > 0) { load_chunk<T, C>(cr, r); load_chunk<T, C>(cr + BN, y); }
             for (int t = steps - 1; t >= 0; t--) {
                 if (t > 0) {
                     cr -= 2 * BN;
@@ -459,36 +473,39 @@ static int sm_count_r() {
 // thread capped at 128 registers (2 CTAs of 256 threads per SM) -- forward 57 ms vs 69-89 ms for the other
 // shapes, adjoint 97 ms (every state stored) / 149 ms (K = 32) vs 106-226 ms.
 template <typename T> static int plan_reg(int B, int N, bool adj, RegPlan* p) {
-    int want = 4;
+    int want = 4, mb = 2;
     const char* e = getenv(adj ? "DHTS_ARZ_C_BWD" : "DHTS_ARZ_C_FWD");     // tuning knob: cells per thread
     if (!e) e = getenv("DHTS_ARZ_C");
     if (e) {
         int c = atoi(e);
-        if (c == 1 || c == 2 || c == 4) want = c;
+        if (c == 1 || c == 2 || c == 4 || c == 8) want = c;
     }
-    int C = (want >= 4 && N % 4 == 0) ? 4 : ((want >= 2 && N % 2 == 0) ? 2 : 1);
+    int C = 1;
+    for (int c = 8; c > 1; c >>= 1)
+        if (want >= c && N % c == 0 && N / c >= 32) { C = c; break; }
     int tpl = N / C;
-    if (tpl > 1024 / C && C > 1) { C = (N % 4 == 0) ? 4 : C; tpl = N / C; }   // long lanes: widest chunk that divides N
-    if (tpl > 1024 / C) return DHTS_ERR_UNSUPPORTED;
-    const int target = 256;                       // threads per CTA when lanes are short
+    while (tpl > 1024 / (C < 4 ? C : 4) && C < 8 && N % (2 * C) == 0) { C *= 2; tpl = N / C; }   // long lanes: wider chunks
+    if (tpl > 1024 / (C < 4 ? C : 4)) return DHTS_ERR_UNSUPPORTED;
+    const int target = 128;                       // threads per CTA when lanes are short
     int lpc = tpl >= target ? 1 : target / tpl;
     if (lpc > B) lpc = B;
     if (lpc < 1) lpc = 1;
     p->C = C; p->lpc = lpc; p->threads = round32(lpc * tpl);
     p->smem = shm_bytes<T>(lpc, p->threads / 32);
     p->grid = (B + lpc - 1) / lpc;
-    p->mb = 2;
-    const char* m = getenv(adj ? "DHTS_ARZ_MB_BWD" : "DHTS_ARZ_MB_FWD");    // tuning knob: min CTAs per SM
+    const char* m = getenv(adj ? "DHTS_ARZ_MB_BWD" : "DHTS_ARZ_MB_FWD");    // tuning knob: register cap, as CTAs of 256 threads per SM
     if (!m) m = getenv("DHTS_ARZ_MB");
-    if (m) p->mb = atoi(m) == 2 ? 2 : 1;
+    if (m) mb = atoi(m) == 2 ? 2 : 1;
+    p->mb = mb;
     return DHTS_OK;
 }
 
-#define DHTS_C_DISPATCH(P, CALL)                                                                     \
-    if ((P).mb == 2) {                                                                               \
-        if ((P).C == 4) { CALL(4, 2) } else if ((P).C == 2) { CALL(2, 2) } else { CALL(1, 1) }       \
-    } else {                                                                                         \
-        if ((P).C == 4) { CALL(4, 1) } else if ((P).C == 2) { CALL(2, 1) } else { CALL(1, 1) }       \
+// MB is the register budget in units of "CTAs of 1024/min(C,4) threads per SM": 2 -> 128 registers, 1 -> 255.
+#define DHTS_C_DISPATCH(P, CALL)                                                                                   \
+    if ((P).mb == 2) {                                                                                             \
+        if ((P).C == 8) { CALL(8, 2) } else if ((P).C == 4) { CALL(4, 2) } else if ((P).C == 2) { CALL(2, 2) } else { CALL(1, 1) } \
+    } else {                                                                                                       \
+        if ((P).C == 8) { CALL(8, 1) } else if ((P).C == 4) { CALL(4, 1) } else if ((P).C == 2) { CALL(2, 1) } else { CALL(1, 1) } \
     }
 
 static int status_r() { return cudaGetLastError() == cudaSuccess ? DHTS_OK : DHTS_ERR_CUDA; }

@@ -195,3 +195,51 @@ def test_long_lane_falls_back_to_step_kernels(dev):
     (rT * T64(w, dev)).sum().backward()
     o = O.arz_rollout(r0, u0, gh, 5.0, 30.0, 0.01, T, g_rT=w)
     assert relerr(rT.detach().cpu(), o["rT"]) < 1e-12 and relerr(tr.grad.cpu(), o["g_r0"]) < 1e-9
+
+
+def test_rollout_cfl_slow_path_and_arena_and_unaligned(dev):
+    """(a) speeds above V/4 but below V = dx/dt: the sufficient CFL tests fail, the exact per-branch test must pass
+    (no flag) and the states stay right; (b) checkpoints written into a caller-owned arena; (c) row starts that are
+    not 16-byte aligned take the tiled per-step kernels -- all three against the oracle."""
+    import dhts_b200
+    from dhts_b200 import functional as F
+    from oracle import oracle as O
+    rng = np.random.default_rng(11)
+    B, N, T, dx, umax, dt = 6, 64, 40, 1.0, 30.0, 0.01          # V = 100, V/4 = 25 < typical u
+    r0 = rng.uniform(0.05, 0.9, (B, N)); u0 = rng.uniform(20.0, 29.0, (B, N))
+    gh = np.stack([rng.uniform(0.1, 0.9, (B, 2)), rng.uniform(20, 29, (B, 2))], -1)
+    w = rng.normal(size=(B, N))
+    o = O.arz_rollout(r0, u0, gh, dx, umax, dt, T, g_rT=w, g_uT=w / umax)
+    assert o["cfl"] == 0
+    arena = torch.empty(T * 2 * B * N + 5, dtype=torch.float64, device=dev)
+    for mode in ("plain", "arena", "unaligned"):
+        flags = dhts_b200.Flags(dev)
+        if mode == "unaligned":
+            big = torch.zeros(B * N + 1, dtype=torch.float64, device=dev)
+            big[1:] = T64(r0, dev).reshape(-1)
+            tr = big[1:].view(B, N).detach().requires_grad_()     # data_ptr is 8 mod 16
+            assert tr.data_ptr() % 16 == 8
+        else:
+            tr = T64(r0, dev).requires_grad_()
+        tu = T64(u0, dev).requires_grad_()
+        rT, yT, uT = F.arz_rollout(tr, tu, T64(gh[:, :, 0], dev), T64(gh[:, :, 1], dev), dx, umax, dt, T, ckpt_every=1,
+                                   flags=flags, ckpt_buffer=arena if mode == "arena" else None)
+        ((rT * T64(w, dev)).sum() + (uT * T64(w / umax, dev)).sum()).backward()
+        assert flags.check()[0] == 0
+        assert relerr(rT.detach().cpu(), o["rT"]) < 1e-11 and relerr(uT.detach().cpu(), o["uT"]) < 1e-11, mode
+        assert relerr(tr.grad.cpu(), o["g_r0"]) < 1e-9 and relerr(tu.grad.cpu(), o["g_u0"]) < 1e-9, mode
+    with pytest.raises(ValueError, match="ckpt_buffer"):
+        F.arz_rollout(T64(r0, dev).requires_grad_(), T64(u0, dev), T64(gh[:, :, 0], dev), T64(gh[:, :, 1], dev), dx, umax,
+                      dt, T, ckpt_every=1, ckpt_buffer=arena[:10])
+
+
+def test_rollout_plan_fits_memory(dev):
+    from dhts_b200 import functional as F
+    chunk, K = F.arz_rollout_plan(65536, 1024, 1000, torch.float64, dev)
+    free, _ = torch.cuda.mem_get_info(dev)
+    assert K == 1 and 296 <= chunk <= 65536 and chunk * 1024 * 1000 * 2 * 8 <= 0.6 * free + 1
+    nchunk = -(-65536 // chunk)
+    assert (nchunk - 1) * chunk < 65536 <= nchunk * chunk
+    assert F.arz_rollout_plan(100, 64, 10, torch.float64, dev) == (100, 1)
+    chunk, K = F.arz_rollout_plan(4096, 1024, 10 ** 7, torch.float64, dev)        # nothing fits: sparse checkpoints
+    assert K == 32 and chunk >= 1
