@@ -28,6 +28,38 @@ namespace dhts {
 
 constexpr unsigned FULL = 0xffffffffu;
 
+// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier: the adjoint's state ring
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "DHTS_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DHTS_DONE;\n"
+        "bra DHTS_WAIT;\n"
+        "DHTS_DONE:\n"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
 // 64-bit shuffles as two explicit 32-bit ones (keeps the register pairs in place)
 __device__ __forceinline__ double shfl_up1(double v) {
     int lo = __shfl_up_sync(FULL, __double2loint(v), 1), hi = __shfl_up_sync(FULL, __double2hiint(v), 1);
@@ -143,6 +175,9 @@ template <typename T> struct Shm {
 template <typename T> __host__ __device__ inline size_t shm_bytes(int lpc, int nwarp) {
     return sizeof(LaneK<T>) * lpc + sizeof(T) * ((size_t)lpc * 2 * (GH_F + GH_A) + (size_t)2 * nwarp * (RF_ADJ + 4)) + 16;
 }
+template <typename T> __host__ __device__ inline size_t ring_offset(int lpc, int nwarp) {
+    return (shm_bytes<T>(lpc, nwarp) + 127) / 128 * 128;
+}
 template <typename T> __device__ __forceinline__ Shm<T> carve_shm(unsigned char* raw, int lpc, int nwarp) {
     Shm<T> s;
     s.lk = reinterpret_cast<LaneK<T>*>(raw);
@@ -175,34 +210,29 @@ __device__ __forceinline__ void setup_group(const Shm<T>& s, int lane0, int nl, 
 // of the last cell is derived up front (the right neighbour needs it); the sweep then derives cell c, solves
 // the interface on its left and finishes the update of cell c-1, so that no per-cell array stays live.
 // STORED: the cells carry an explicitly stored speed (set_r_u, step 0).  CHECK: evaluate the CFL condition.
-template <typename T, bool STORED>
+// The sweep exists twice: VAC = false is taken when no cell it touches is below eps (every step of a run
+// without vacuum) and drops the clamps, the vacuum predicates and the vacuum fix-ups.
+template <typename T, bool STORED, bool VAC>
 __device__ __forceinline__ FRec<T> fcell(T r, T y, T us, const LaneK<T>& k) {
-    FRec<T> c = fderive<T, STORED>(r, y, us, k);
-    if (r < DHTS_EPS) c.w = w_vacuum(r, c.us, k);      // rare
+    FRec<T> c = fderive<T, STORED, VAC>(r, y, us, k);
+    if (VAC) {
+        if (r < DHTS_EPS) c.w = w_vacuum(r, c.us, k);      // rare
+    }
     return c;
 }
 
-template <typename T, int C, bool STORED, bool CHECK>
-__device__ __forceinline__ bool chunk_fwd_step(T* r, T* y, const T* us, bool first_chunk, bool last_chunk,
-                                               const LaneK<T>& k, const T* ghostL, const T* ghostR, T dt, T* boxL,
-                                               T* boxR, int warp, int nwarp, unsigned lane) {
-    const FRec<T> last = fcell<T, STORED>(r[C - 1], y[C - 1], STORED ? us[C - 1] : T(0), k);
-    T mine[RF_FWD], left[RF_FWD];
-    pack(last, mine);
-    from_left<T, RF_FWD>(mine, left, boxL, warp, lane);
-    FRec<T> L = first_chunk ? unpack_f(ghostL) : unpack_f(left);
-    bool okL = CHECK ? cell_speed_ok(L.us, L.w, k) : true;
+template <typename T, int C, bool STORED, bool CHECK, bool VAC>
+__device__ __forceinline__ bool chunk_fwd_sweep(T* r, T* y, const T* us, const FRec<T>& last, FRec<T>& L,
+                                                const LaneK<T>& k, T dt, T* f0, T& fpr, T& fpy, bool& okL) {
     bool bad = false;
-    T f0[2], fpr = T(0), fpy = T(0);
 #pragma unroll
     for (int c = 0; c < C; c++) {
-        const FRec<T> cur = (c == C - 1) ? last : fcell<T, STORED>(r[c], y[c], STORED ? us[c] : T(0), k);
+        const FRec<T> cur = (c == C - 1) ? last : fcell<T, STORED, VAC>(r[c], y[c], STORED ? us[c] : T(0), k);
         T fr, fy;
-        bool sus = false;
-        fflux(L, cur.r, cur.us, k, fr, fy, sus);
+        fflux<T, VAC>(L, cur.r, cur.us, k, fr, fy);
         if (CHECK) {
             const bool okR = cell_speed_ok(cur.us, cur.w, k);
-            if (sus || !okL || !okR) bad |= cfl_exact_bad(L.r, L.us, L.sq, L.w, cur.r, cur.us, k, dt);   // never in a valid run
+            if (!okL || !okR) bad |= cfl_exact_bad(L.r, L.us, L.sq, L.w, cur.r, cur.us, k, dt);   // never in a valid run
             okL = okR;
         }
         if (c == 0) { f0[0] = fr; f0[1] = fy; }
@@ -212,14 +242,33 @@ __device__ __forceinline__ bool chunk_fwd_step(T* r, T* y, const T* us, bool fir
         }
         fpr = fr; fpy = fy; L = cur;
     }
+    return bad;
+}
+
+template <typename T, int C, bool STORED, bool CHECK>
+__device__ __forceinline__ bool chunk_fwd_step(T* r, T* y, const T* us, bool first_chunk, bool last_chunk,
+                                               const LaneK<T>& k, const T* ghostL, const T* ghostR, T dt, T* boxL,
+                                               T* boxR, int warp, int nwarp, unsigned lane) {
+    const FRec<T> last = fcell<T, STORED, true>(r[C - 1], y[C - 1], STORED ? us[C - 1] : T(0), k);
+    T mine[RF_FWD], left[RF_FWD];
+    pack(last, mine);
+    from_left<T, RF_FWD>(mine, left, boxL, warp, lane);
+    FRec<T> L = first_chunk ? unpack_f(ghostL) : unpack_f(left);
+    bool okL = CHECK ? cell_speed_ok(L.us, L.w, k) : true;
+    bool anyvac = L.r < DHTS_EPS;
+#pragma unroll
+    for (int c = 0; c < C; c++) anyvac |= r[c] < DHTS_EPS;
+    T f0[2], fpr = T(0), fpy = T(0);
+    bool bad;
+    if (anyvac) bad = chunk_fwd_sweep<T, C, STORED, CHECK, true>(r, y, us, last, L, k, dt, f0, fpr, fpy, okL);
+    else bad = chunk_fwd_sweep<T, C, STORED, CHECK, false>(r, y, us, last, L, k, dt, f0, fpr, fpy, okL);
     T fR[2];
     from_right<T, 2>(f0, fR, boxR, warp, nwarp, lane);
     if (last_chunk) {   // interface with the right ghost cell
         const FRec<T> G = unpack_f(ghostR);
-        bool sus = false;
-        fflux(L, G.r, G.us, k, fR[0], fR[1], sus);
+        fflux<T, true>(L, G.r, G.us, k, fR[0], fR[1]);
         if (CHECK) {
-            if (sus || !okL || !cell_speed_ok(G.us, G.w, k)) bad |= cfl_exact_bad(L.r, L.us, L.sq, L.w, G.r, G.us, k, dt);
+            if (!okL || !cell_speed_ok(G.us, G.w, k)) bad |= cfl_exact_bad(L.r, L.us, L.sq, L.w, G.r, G.us, k, dt);
         }
     }
     r[C - 1] = fma(fpr - fR[0], k.cc, r[C - 1]);
@@ -228,7 +277,7 @@ __device__ __forceinline__ bool chunk_fwd_step(T* r, T* y, const T* us, bool fir
 }
 
 template <typename T, int C, int MB>
-__global__ void __launch_bounds__(1024 / C, (C == 8 ? 2 : 1) * MB) arz_rollout_fwd_reg_kernel(const T* __restrict__ r0, const T* __restrict__ y0,
+__global__ void __launch_bounds__(1024 / (C < 4 ? C : 4), MB) arz_rollout_fwd_reg_kernel(const T* __restrict__ r0, const T* __restrict__ y0,
                                            const T* __restrict__ u0, const T* __restrict__ ghost,
                                            const T* __restrict__ dx, const T* __restrict__ umax_, T dt, int B, int N,
                                            int steps, int K, int lpc, T* __restrict__ ckpt, T* __restrict__ rT,
@@ -287,32 +336,26 @@ __global__ void __launch_bounds__(1024 / C, (C == 8 ? 2 : 1) * MB) arz_rollout_f
 // One adjoint step of this thread's chunk: (gr, gy) <- VJP of the step taken from state (r, y)
 // (flux-difference form of dmacro_lane.py:293-303), streamed like the forward step: interface c
 // gives A^T w to cell c-1 and B^T w to cell c, so cell c-1 is finished as soon as interface c is done.
-// accL / accR collect the ghost adjoints.
-template <typename T, bool STORED>
+// accL / accR collect the ghost adjoints.  VAC as in the forward sweep.
+template <typename T, bool STORED, bool VAC>
 __device__ __forceinline__ ARec<T> acell(T r, T y, T us, const LaneK<T>& k) {
-    ARec<T> c = aderive<T, STORED>(r, y, us, k);
-    if (r < DHTS_EPS) fix_vacuum_adj(c, y, k);         // rare
+    ARec<T> c = aderive<T, STORED, VAC>(r, y, us, k);
+    if (VAC) {
+        if (r < DHTS_EPS) fix_vacuum_adj(c, y, k);         // rare
+    }
     return c;
 }
 
-template <typename T, int C, bool STORED>
-__device__ __forceinline__ bool chunk_adj_step(const T* r, const T* y, const T* us, T* gr, T* gy, bool first_chunk,
-                                               bool last_chunk, const LaneK<T>& k, const T* ghostL, const T* ghostR,
-                                               T* accL, T* accR, T* boxL, T* boxR, int warp, int nwarp, unsigned lane) {
-    const ARec<T> last = acell<T, STORED>(r[C - 1], y[C - 1], STORED ? us[C - 1] : T(0), k);
-    T mine[RF_ADJ], left[RF_ADJ];
-    pack(last, gr[C - 1], gy[C - 1], mine);
-    from_left<T, RF_ADJ>(mine, left, boxL, warp, lane);
-    ARec<T> L = first_chunk ? unpack_a(ghostL) : unpack_a(left);
-    T gLr = first_chunk ? T(0) : left[10], gLy = first_chunk ? T(0) : left[11];   // OLD adjoint of the cell on the left
-    T a0[2], bpr = T(0), bpy = T(0);
+template <typename T, int C, bool STORED, bool VAC>
+__device__ __forceinline__ bool chunk_adj_sweep(const T* r, const T* y, const T* us, T* gr, T* gy, const ARec<T>& last,
+                                                ARec<T>& L, T& gLr, T& gLy, const LaneK<T>& k, T* a0, T& bpr, T& bpy) {
     bool nan = false;
 #pragma unroll
     for (int c = 0; c < C; c++) {
-        const ARec<T> cur = (c == C - 1) ? last : acell<T, STORED>(r[c], y[c], STORED ? us[c] : T(0), k);
+        const ARec<T> cur = (c == C - 1) ? last : acell<T, STORED, VAC>(r[c], y[c], STORED ? us[c] : T(0), k);
         const T gcr = gr[c], gcy = gy[c];
         T ar, ay, br, by;
-        aflux(L, cur, gcr - gLr, gcy - gLy, k, ar, ay, br, by);
+        aflux<T, VAC>(L, cur, gcr - gLr, gcy - gLy, k, ar, ay, br, by);
         if (c == 0) { a0[0] = ar; a0[1] = ay; }
         else {
             gr[c - 1] = fma(k.cc, ar + bpr, gLr);
@@ -321,12 +364,33 @@ __device__ __forceinline__ bool chunk_adj_step(const T* r, const T* y, const T* 
         }
         bpr = br; bpy = by; L = cur; gLr = gcr; gLy = gcy;
     }
+    return nan;
+}
+
+template <typename T, int C, bool STORED>
+__device__ __forceinline__ bool chunk_adj_step(const T* r, const T* y, const T* us, T* gr, T* gy, bool first_chunk,
+                                               bool last_chunk, const LaneK<T>& k, const T* ghostL, const T* ghostR,
+                                               T* accL, T* accR, T* boxL, T* boxR, int warp, int nwarp, unsigned lane) {
+    const T rl = r[C - 1];
+    const ARec<T> last = acell<T, STORED, true>(rl, y[C - 1], STORED ? us[C - 1] : T(0), k);
+    T mine[RF_ADJ], left[RF_ADJ];
+    pack(last, gr[C - 1], gy[C - 1], mine);
+    from_left<T, RF_ADJ>(mine, left, boxL, warp, lane);
+    ARec<T> L = first_chunk ? unpack_a(ghostL) : unpack_a(left);
+    T gLr = first_chunk ? T(0) : left[10], gLy = first_chunk ? T(0) : left[11];   // OLD adjoint of the cell on the left
+    T a0[2], bpr = T(0), bpy = T(0);
+    bool anyvac = (L.r < DHTS_EPS) || (rl < DHTS_EPS);
+#pragma unroll
+    for (int c = 0; c < C - 1; c++) anyvac |= r[c] < DHTS_EPS;
+    bool nan;
+    if (anyvac) nan = chunk_adj_sweep<T, C, STORED, true>(r, y, us, gr, gy, last, L, gLr, gLy, k, a0, bpr, bpy);
+    else nan = chunk_adj_sweep<T, C, STORED, false>(r, y, us, gr, gy, last, L, gLr, gLy, k, a0, bpr, bpy);
     T aR[2];
     from_right<T, 2>(a0, aR, boxR, warp, nwarp, lane);
     if (last_chunk) {   // interface with the right ghost (its updated-state adjoint is zero)
         const ARec<T> G = unpack_a(ghostR);
         T pbr, pby;
-        aflux(L, G, -gLr, -gLy, k, aR[0], aR[1], pbr, pby);
+        aflux<T, true>(L, G, -gLr, -gLy, k, aR[0], aR[1], pbr, pby);
         accR[0] = fma(k.cc, pbr, accR[0]); accR[1] = fma(k.cc, pby, accR[1]);
     }
     if (first_chunk) { accL[0] = fma(k.cc, a0[0], accL[0]); accL[1] = fma(k.cc, a0[1], accL[1]); }
@@ -336,19 +400,36 @@ __device__ __forceinline__ bool chunk_adj_step(const T* r, const T* y, const T* 
     return nan;
 }
 
-template <typename T, int C, int MB>
-__global__ void __launch_bounds__(1024 / C, (C == 8 ? 2 : 1) * MB) arz_rollout_bwd_reg_kernel(const T* __restrict__ ckpt, const T* __restrict__ u0,
+// MODE 0: every state stored, streamed back through the TMA ring;  1: every state stored, register prefetch;
+// 2: checkpoint every K steps, segment recompute with an L2-resident stash.  (Separate instantiations so that
+// each gets its own register allocation.)
+template <typename T, int C, int MB, int MODE>
+__global__ void __launch_bounds__(1024 / (C < 4 ? C : 4), MB) arz_rollout_bwd_reg_kernel(const T* __restrict__ ckpt, const T* __restrict__ u0,
                                            const T* __restrict__ ghost, const T* __restrict__ dx,
                                            const T* __restrict__ umax_, T dt, int B, int N, int steps, int K, int lpc,
                                            const T* __restrict__ rT, const T* __restrict__ yT,
                                            const T* __restrict__ g_rT, const T* __restrict__ g_yT,
                                            const T* __restrict__ g_uT, T* __restrict__ scratch,
                                            T* __restrict__ g_r0, T* __restrict__ g_y0, T* __restrict__ g_ghost,
-                                           int* __restrict__ flags) {
-    extern __shared__ __align__(16) unsigned char raw[];
+                                           int* __restrict__ flags, int ring_ns) {
+    extern __shared__ __align__(128) unsigned char raw[];
     const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5;
     const unsigned lane = threadIdx.x & 31;
     Shm<T> s = carve_shm<T>(raw, lpc, nwarp);
+    // state ring of the every-state-stored adjoint: ring_ns stages of (r row, y row) of the CTA's lanes, filled by
+    // TMA bulk copies that complete on one mbarrier per stage
+    const size_t stage_elems = (size_t)2 * lpc * N;
+    T* ring = reinterpret_cast<T*>(raw + ring_offset<T>(lpc, nwarp));
+    uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)ring_ns * stage_elems);
+    if (MODE == 0) {
+        if (threadIdx.x == 0) {
+            for (int i = 0; i < ring_ns; i++) mbar_init(full + i, 1);
+            mbar_init_fence();
+        }
+        __syncthreads();
+    }
+    int fill_st = 0, use_st = 0;              // next stage to fill (thread 0) / to consume (all threads)
+    unsigned use_par = 0;
     const int tpl = N / C;
     const int l = threadIdx.x / tpl, kc = threadIdx.x - l * tpl;
     const int ngroup = (B + lpc - 1) / lpc;
@@ -385,8 +466,45 @@ __global__ void __launch_bounds__(1024 / C, (C == 8 ? 2 : 1) * MB) arz_rollout_b
         T* blA = s.boxL; T* blB = s.boxL + nwarp * RF_ADJ;
         T* brA = s.boxR; T* brB = s.boxR + nwarp * 4;
 #define DHTS_SWAP_BOXES { T* x_ = blA; blA = blB; blB = x_; x_ = brA; brA = brB; brB = x_; }
-        if (K == 1) {
-            // every state was stored by the forward pass: stream them back, one step ahead of the arithmetic
+        if (MODE == 0) {
+            // every state was stored by the forward pass: one thread streams the rows of the CTA's lanes back through
+            // the shared-memory ring, ring_ns steps ahead of the arithmetic.  A stage is refilled at the top of the
+            // step after the one that consumed it: by then every thread has passed that step's two block barriers,
+            // i.e. has finished reading the stage.
+            const unsigned rowbytes = (unsigned)((size_t)nl * N * sizeof(T));
+            const T* src0 = ckpt + (size_t)lane0 * N;
+            int issued = 0;
+#define DHTS_RING_ISSUE                                                                                  \
+            {                                                                                            \
+                uint64_t* bar_ = full + fill_st;                                                         \
+                T* dst_ = ring + (size_t)fill_st * stage_elems;                                          \
+                const T* src_ = src0 + (size_t)(steps - 1 - issued) * 2 * BN;                            \
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                             \
+                mbar_expect_tx(bar_, 2 * rowbytes);                                                      \
+                bulk_g2s(dst_, src_, rowbytes, bar_);                                                    \
+                bulk_g2s(dst_ + (size_t)lpc * N, src_ + BN, rowbytes, bar_);                             \
+                issued++;                                                                                \
+                if (++fill_st == ring_ns) fill_st = 0;                                                   \
+            }
+            if (threadIdx.x == 0)
+                while (issued < ring_ns && issued < steps) DHTS_RING_ISSUE
+            for (int t = steps - 1; t >= 0; t--) {
+                if (threadIdx.x == 0 && t != steps - 1 && issued < steps) DHTS_RING_ISSUE
+                mbar_wait(full + use_st, use_par);
+                // cells are read from the stage where the sweep needs them (no register copy of the chunk); the
+                // last read precedes the step's second block barrier
+                const T* r = ring + (size_t)use_st * stage_elems + soff;
+                const T* y = r + (size_t)lpc * N;
+                if (++use_st == ring_ns) { use_st = 0; use_par ^= 1u; }
+                if (t == 0 && u0)
+                    { T us_[C]; load_chunk<T, C>(u0 + off, us_); nan |= chunk_adj_step<T, C, true>(r, y, us_, gr, gy, first_chunk, last_chunk, k, gLa, gRa, accL, accR, blA, brA, warp, nwarp, lane); }
+                else
+                    nan |= chunk_adj_step<T, C, false>(r, y, nullptr, gr, gy, first_chunk, last_chunk, k, gLa, gRa, accL, accR, blA, brA, warp, nwarp, lane);
+                DHTS_SWAP_BOXES
+            }
+#undef DHTS_RING_ISSUE
+        } else if (MODE == 1) {
+            // register-prefetch variant (rows not 16-byte sized, or no room for the ring): one step ahead of the arithmetic
             // (measured: prefetching only into L2 and loading at the top of the step is 15 % slower)
             T r[C], y[C], rn[C], yn[C];
             const T* cr = ckpt + (size_t)(steps > 0 ? steps - 1 : 0) * 2 * BN + off;
@@ -453,7 +571,7 @@ __global__ void __launch_bounds__(1024 / C, (C == 8 ? 2 : 1) * MB) arz_rollout_b
 
 // ------------------------------------------------------------------ host-side planning and launch
 
-struct RegPlan { int C, lpc, threads, grid, mb; size_t smem; };
+struct RegPlan { int C, lpc, threads, grid, ring_ns, mode; size_t smem; };
 
 static int round32(int x) { return (x + 31) / 32 * 32; }
 // vector chunk loads need 16-byte aligned bases (row offsets are multiples of C elements by construction)
@@ -473,7 +591,7 @@ static int sm_count_r() {
 // thread capped at 128 registers (2 CTAs of 256 threads per SM) -- forward 57 ms vs 69-89 ms for the other
 // shapes, adjoint 97 ms (every state stored) / 149 ms (K = 32) vs 106-226 ms.
 template <typename T> static int plan_reg(int B, int N, bool adj, RegPlan* p) {
-    int want = 4, mb = 2;
+    int want = 4;
     const char* e = getenv(adj ? "DHTS_ARZ_C_BWD" : "DHTS_ARZ_C_FWD");     // tuning knob: cells per thread
     if (!e) e = getenv("DHTS_ARZ_C");
     if (e) {
@@ -493,20 +611,35 @@ template <typename T> static int plan_reg(int B, int N, bool adj, RegPlan* p) {
     p->C = C; p->lpc = lpc; p->threads = round32(lpc * tpl);
     p->smem = shm_bytes<T>(lpc, p->threads / 32);
     p->grid = (B + lpc - 1) / lpc;
-    const char* m = getenv(adj ? "DHTS_ARZ_MB_BWD" : "DHTS_ARZ_MB_FWD");    // tuning knob: register cap, as CTAs of 256 threads per SM
-    if (!m) m = getenv("DHTS_ARZ_MB");
-    if (m) mb = atoi(m) == 2 ? 2 : 1;
-    p->mb = mb;
+    // Adjoint with every state stored: shared-memory ring for the state rows (TMA bulk copies need 16-byte rows).
+    // Budget per CTA keeps two CTAs of the 128-register shape on an SM (227 KB usable, 1 KB reserved per CTA).
+    p->ring_ns = 0; p->mode = 1;
+    if (adj) {
+        const size_t stage = (size_t)2 * lpc * N * sizeof(T);
+        const size_t base = ring_offset<T>(lpc, p->threads / 32);
+        const size_t budget = (C > 1 ? 112 : 224) * (size_t)1024;
+        int ns = 4;
+        const char* rg = getenv("DHTS_ARZ_RING");              // tuning knob: ring stages (0 = register prefetch)
+        if (rg) ns = atoi(rg);
+        if (ns > 8) ns = 8;
+        while (ns >= 2 && base + ns * (stage + 8) > budget) ns--;
+        if (ns >= 2 && ((size_t)N * sizeof(T)) % 16 == 0 && (size_t)lpc * N * sizeof(T) < (1u << 19)) {
+            p->ring_ns = ns; p->mode = 0;
+            p->smem = base + ns * (stage + 8);
+        }
+    }
     return DHTS_OK;
 }
 
-// MB is the register budget in units of "CTAs of 1024/min(C,4) threads per SM": 2 -> 128 registers, 1 -> 255.
+// MB is the register budget in units of "CTAs of 1024/min(C,4) threads per SM": 2 -> 128 registers (measured best
+// for every C > 1, profiles/r1e sweep), 1 -> 255.
 #define DHTS_C_DISPATCH(P, CALL)                                                                                   \
-    if ((P).mb == 2) {                                                                                             \
-        if ((P).C == 8) { CALL(8, 2) } else if ((P).C == 4) { CALL(4, 2) } else if ((P).C == 2) { CALL(2, 2) } else { CALL(1, 1) } \
-    } else {                                                                                                       \
-        if ((P).C == 8) { CALL(8, 1) } else if ((P).C == 4) { CALL(4, 1) } else if ((P).C == 2) { CALL(2, 1) } else { CALL(1, 1) } \
-    }
+    if ((P).C == 8) { CALL(8, 2) } else if ((P).C == 4) { CALL(4, 2) } else if ((P).C == 2) { CALL(2, 2) } else { CALL(1, 1) }
+#define CALL0(CC, MB) CALLM(CC, MB, 0)
+#define CALL1(CC, MB) CALLM(CC, MB, 1)
+#define CALL2(CC, MB) CALLM(CC, MB, 2)
+#define DHTS_CM_DISPATCH(P)                                                                                        \
+    if ((P).mode == 0) { DHTS_C_DISPATCH(P, CALL0) } else if ((P).mode == 1) { DHTS_C_DISPATCH(P, CALL1) } else { DHTS_C_DISPATCH(P, CALL2) }
 
 static int status_r() { return cudaGetLastError() == cudaSuccess ? DHTS_OK : DHTS_ERR_CUDA; }
 
@@ -530,11 +663,25 @@ static int rollout_fwd(const T* r0, const T* y0, const T* u0, const T* ghost, co
     return status_r();
 }
 
+// adjoint mode (see the kernel): recompute when K > 1, else the ring when it was planned and applies
+template <typename T> static void set_mode(RegPlan* p, int K, bool ring_ok) {
+    if (K == 1 && ring_ok && p->ring_ns > 0 && p->C > 1) { p->mode = 0; return; }
+    p->ring_ns = 0; p->mode = K > 1 ? 2 : 1;
+    p->smem = shm_bytes<T>(p->lpc, p->threads / 32);
+}
+
 template <typename T> static int bwd_grid_r(const RegPlan& p) {
     int occ = 0;
-#define CALL(CC, MB) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, arz_rollout_bwd_reg_kernel<T, CC, MB>, p.threads, p.smem);
-    DHTS_C_DISPATCH(p, CALL)
-#undef CALL
+#define CALLM(CC, MB, MD)                                                                                              \
+    {                                                                                                                  \
+        if (p.smem > 48 * 1024)                                                                                        \
+            cudaFuncSetAttribute(arz_rollout_bwd_reg_kernel<T, CC, MB, MD>,                                            \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);                            \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, arz_rollout_bwd_reg_kernel<T, CC, MB, MD>, p.threads,      \
+                                                      p.smem);                                                         \
+    }
+    DHTS_CM_DISPATCH(p)
+#undef CALLM
     if (occ < 1) occ = 1;
     long long g = (long long)sm_count_r() * occ;
     return (int)(g < p.grid ? g : p.grid);
@@ -545,6 +692,7 @@ template <typename T> static long long rollout_scratch_elems(int B, int N, int K
     if (B <= 0) return 0;
     if (K < 1 || plan_reg<T>(B, N, true, &p)) return -1;
     if (K == 1) return 0;                      // every state comes from the forward pass: nothing to stash
+    set_mode<T>(&p, K, false);
     return (long long)bwd_grid_r<T>(p) * K * 2 * p.lpc * N;
 }
 
@@ -561,11 +709,20 @@ static int rollout_bwd(const T* ckpt, const T* u0, const T* ghost, const T* dx, 
     int rc = plan_reg<T>(B, N, true, &p);
     if (rc) return rc;
     if (p.C > 1 && !(al16(ckpt) && al16(u0) && al16(scratch) && al16(g_r0) && al16(g_y0))) return DHTS_ERR_UNSUPPORTED;
+    set_mode<T>(&p, K, al16(ckpt));
     int grid = bwd_grid_r<T>(p);
     if (K > 1 && (long long)grid * K * 2 * p.lpc * N > scratch_elems) return DHTS_ERR_INVALID;
-#define CALL(CC, MB) arz_rollout_bwd_reg_kernel<T, CC, MB><<<grid, p.threads, p.smem, st>>>(ckpt, u0, ghost, dx, umax, dt, B, N, steps, K, p.lpc, rT, yT, g_rT, g_yT, g_uT, scratch, g_r0, g_y0, g_ghost, flags);
-    DHTS_C_DISPATCH(p, CALL)
-#undef CALL
+#define CALLM(CC, MB, MD)                                                                                              \
+    {                                                                                                                  \
+        if (p.smem > 48 * 1024)                                                                                        \
+            cudaFuncSetAttribute(arz_rollout_bwd_reg_kernel<T, CC, MB, MD>,                                            \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);                            \
+        arz_rollout_bwd_reg_kernel<T, CC, MB, MD><<<grid, p.threads, p.smem, st>>>(                                    \
+            ckpt, u0, ghost, dx, umax, dt, B, N, steps, K, p.lpc, rT, yT, g_rT, g_yT, g_uT, scratch, g_r0, g_y0,       \
+            g_ghost, flags, p.ring_ns);                                                                                \
+    }
+    DHTS_CM_DISPATCH(p)
+#undef CALLM
     return status_r();
 }
 

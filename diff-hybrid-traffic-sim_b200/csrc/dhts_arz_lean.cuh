@@ -16,9 +16,13 @@
 // CFL.  The reference asserts dt < dx / max(|s|, 1e-5) for two wave speeds per interface
 // (_macro_lane.py:137-146), i.e. |s| < dx/dt =: V.  Every non-shock speed is an average of
 // u, w = u_max + u - u_eq and lambda_0 = u - (u_max/2) sqrt(r) of the two cells, so two
-// per-cell tests (|u| < V/4, |w| < V/4, which bound (u_max/2) sqrt(r) too) plus one exact test of the
-// shock speed imply all of them.  Only when one of these SUFFICIENT tests fails (never in a
-// run the reference would accept) is the exact per-branch evaluation done (cfl_exact).
+// per-cell tests (|u| < V/4, |w| < V/4, which bound (u_max/2) sqrt(r) too) imply them.  The shock
+// speed (u_L > u_R, r_L >= eps) is s = fd / max(r_m - r_L, eps) with fd = r_m u_R - r_L u_L and
+// r_m - r_L = (du/u_max)(2 sqrt(r_L) + du/u_max), du = u_L - u_R > 0, hence
+//   fd / (r_m - r_L) = u_R - r_L u_max / (2 sqrt(r_L) + du/u_max),   |.| <= |u_R| + (u_max/2) sqrt(r_L) < V/2,
+// and clamping the denominator up to eps only shrinks |s|: the same two per-cell tests cover it.
+// Only when one of these SUFFICIENT tests fails (never in a run the reference would accept) is the
+// exact per-branch evaluation done (cfl_exact_bad).
 //
 // Adjoint.  With z = F'(Q0)^T w, k = (u0 - u_eq0) - r0 u_eq'(r0), s = z0 + k z1 and
 // a = 2 sqrt(r0), the products dQ0/dQ_L^T z and dQ0/dQ_R^T z of darz.py collapse to
@@ -68,10 +72,11 @@ template <typename T> __device__ __forceinline__ bool cell_speed_ok(T us, T w, c
 
 // Per-cell record.  STORED: the cell carries an explicitly stored speed (ghosts, set_r_u at step 0).
 // Cells below eps need fix_vacuum afterwards (u_eq(r) = u_max(1 - sqrt(max(r,0)+eps)) differs from the clamped one).
-template <typename T, bool STORED>
+// VAC = false: the caller guarantees r >= eps (no clamp, no vacuum handling).
+template <typename T, bool STORED, bool VAC = true>
 __device__ __forceinline__ FRec<T> fderive(T r, T y, T us_in, const LaneK<T>& k) {
     FRec<T> c;
-    const T rc = t_max(r, DHTS_EPS);
+    const T rc = VAC ? t_max(r, DHTS_EPS) : r;
     const T rs = f_rsqrt(rc);
     const T ri = rs * rs;
     const T se = f_sqrt_pos(rc + DHTS_EPS);
@@ -91,10 +96,10 @@ template <typename T> __device__ __forceinline__ T w_vacuum(T r, T us, const Lan
 // Outcome predicates of the case tree (_arz.py:225-322), shared by forward and adjoint.
 template <typename T> struct Tree { bool isL, isM, shock; T b, sc, q, rm, fd; };
 
-template <typename T>
+template <typename T, bool VAC = true>
 __device__ __forceinline__ Tree<T> case_tree(T Lr, T Lus, T Lsq, T Lw, T Rr, T Rus, const LaneK<T>& k) {
     Tree<T> t;
-    const bool vacL = Lr < DHTS_EPS, vacR = Rr < DHTS_EPS;
+    const bool vacL = VAC && Lr < DHTS_EPS, vacR = VAC && Rr < DHTS_EPS;
     const T du = Lus - Rus;
     const bool same = t_abs(du) < DHTS_EPS;
     const bool shock = du > T(0);
@@ -136,9 +141,9 @@ __device__ __forceinline__ bool cfl_exact_bad(T Lr, T Lus, T Lsq, T Lw, T Rr, T 
 }
 
 // Flux through the interface between cell L (record) and a right cell (r, stored speed).
-template <typename T>
-__device__ __forceinline__ void fflux(const FRec<T>& L, T Rr, T Rus, const LaneK<T>& k, T& fr, T& fy, bool& suspect) {
-    const Tree<T> t = case_tree(L.r, L.us, L.sq, L.w, Rr, Rus, k);
+template <typename T, bool VAC = true>
+__device__ __forceinline__ void fflux(const FRec<T>& L, T Rr, T Rus, const LaneK<T>& k, T& fr, T& fy) {
+    const Tree<T> t = case_tree<T, VAC>(L.r, L.us, L.sq, L.w, Rr, Rus, k);
     const T root = t.isM ? t.b : t.q;
     const T r0 = root * root;
     const T u0 = t.isM ? Rus : t.sc * (T(0.5) / T(1.5));
@@ -146,9 +151,6 @@ __device__ __forceinline__ void fflux(const FRec<T>& L, T Rr, T Rus, const LaneK
     const T y0 = r0 * (u0 - ueq);
     fr = t.isL ? L.fr : r0 * u0;
     fy = t.isL ? L.fy : y0 * u0;
-    // shock speed (only where u_L > u_R): |fd| / max(rm - r_L, eps) < V  <=>  |fd| < V (rm - r_L)  or  |fd| < V eps
-    const T afd = t_abs(t.fd);
-    suspect |= t.shock && !((afd < k.vmax * (t.rm - L.r)) || (afd < k.veps));
 }
 
 // ---------------------------------------------------------------------------- adjoint
@@ -167,10 +169,10 @@ template <typename T> __device__ __forceinline__ ARec<T> unpack_a(const T* a) {
 }
 
 // Cells below eps need fix_vacuum_adj afterwards.
-template <typename T, bool STORED>
+template <typename T, bool STORED, bool VAC = true>
 __device__ __forceinline__ ARec<T> aderive(T r, T y, T us_in, const LaneK<T>& k) {
     ARec<T> c;
-    const T rc = t_max(r, DHTS_EPS);
+    const T rc = VAC ? t_max(r, DHTS_EPS) : r;
     const T rs = f_rsqrt(rc);
     const T ri = rs * rs;
     const T se = f_sqrt_pos(rc + DHTS_EPS);
@@ -195,10 +197,10 @@ template <typename T> __device__ __forceinline__ void fix_vacuum_adj(ARec<T>& c,
 }
 
 // A^T w -> (par, pay) for the left cell, B^T w -> (pbr, pby) for the right cell (see header).
-template <typename T>
+template <typename T, bool VAC = true>
 __device__ __forceinline__ void aflux(const ARec<T>& L, const ARec<T>& R, T wr, T wy, const LaneK<T>& k, T& par,
                                       T& pay, T& pbr, T& pby) {
-    const Tree<T> t = case_tree(L.r, L.us, L.sq, L.w, R.r, R.us, k);
+    const Tree<T> t = case_tree<T, VAC>(L.r, L.us, L.sq, L.w, R.r, R.us, k);
     const T root = t.isM ? t.b : t.q;
     const T r0 = root * root;
     const T rootr = t_abs(root);

@@ -125,7 +125,8 @@ def test_rollout_vs_golden_fp32(dev):
 
 
 @pytest.mark.parametrize("B,N,T,K", [(1, 10, 500, 32), (37, 10, 60, 8), (5, 100, 50, 16), (3, 1024, 24, 8),
-                                      (300, 33, 20, 5)])
+                                      (300, 33, 20, 5), (3, 1024, 24, 1), (301, 64, 20, 1), (5, 128, 3, 1),
+                                      (700, 1024, 6, 1), (2, 4096, 5, 1)])
 def test_rollout_vs_oracle_shapes(dev, B, N, T, K):
     """C1's shape (1 x 10 x 500), many short lanes per CTA, C5's lane shape (1024 cells), ragged groups."""
     import dhts_b200
@@ -147,6 +148,38 @@ def test_rollout_vs_oracle_shapes(dev, B, N, T, K):
     assert relerr(rT.detach().cpu(), o["rT"]) < 1e-9 and relerr(uT.detach().cpu(), o["uT"]) < 1e-9
     assert relerr(tr.grad.cpu(), o["g_r0"]) < 1e-8 and relerr(tu.grad.cpu(), o["g_u0"]) < 1e-8
     assert relerr(torch.stack([tgr.grad, tgu.grad], -1).cpu(), o["g_ghost"]) < 1e-8
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_rollout_ring_equals_register_prefetch(dev, dtype):
+    """Every-state-stored adjoint: the TMA ring variant (state rows staged in shared memory by cp.async.bulk) and the
+    register-prefetch variant do the same arithmetic, so gradients must agree to rounding (observed: bitwise or 1 ulp) -- persistent loop over
+    more lane groups than CTAs, ragged last group, fewer steps than ring stages, stored-speed first step."""
+    import os
+    import dhts_b200
+    from dhts_b200 import functional as F
+    rng = np.random.default_rng(5)
+    for B, N, T in ((701, 1024, 7), (301, 64, 9), (9, 256, 2), (40, 2048, 5)):
+        r0 = rng.uniform(0, 1, (B, N)); u0 = rng.uniform(0, 30, (B, N))
+        gr = rng.uniform(0, 1, (B, 2)); gu = rng.uniform(0, 30, (B, 2)); w = rng.normal(size=(B, N))
+        t = lambda a: torch.tensor(a, dtype=dtype, device=dev)
+        out = {}
+        for ring in ("4", "2", "0"):
+            os.environ["DHTS_ARZ_RING"] = ring
+            try:
+                flags = dhts_b200.Flags(dev)
+                tr, tu = t(r0).requires_grad_(), t(u0).requires_grad_()
+                tgr, tgu = t(gr).requires_grad_(), t(gu).requires_grad_()
+                rT, yT, uT = F.arz_rollout(tr, tu, tgr, tgu, 5.0, 30.0, 0.01, T, ckpt_every=1, flags=flags)
+                ((rT * t(w)).sum() + (uT * t(w / 30)).sum()).backward()
+                flags.check()
+                out[ring] = [x.clone() for x in (tr.grad, tu.grad, tgr.grad, tgu.grad)]
+            finally:
+                del os.environ["DHTS_ARZ_RING"]
+        tol = 1e-13 if dtype == torch.float64 else 1e-5       # same arithmetic; the compiler may contract differently
+        for ring in ("4", "2"):
+            for a, b in zip(out[ring], out["0"]):
+                assert relerr(a.cpu(), b.cpu()) < tol, (B, N, T, ring)
 
 
 def test_rollout_equals_chained_steps(dev):
