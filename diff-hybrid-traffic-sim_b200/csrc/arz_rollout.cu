@@ -46,6 +46,17 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// shared -> global bulk store, tracked by bulk async-groups (SASS UBLKCP.G.S)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N_> __device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N_) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
     asm volatile(
         "{\n"
@@ -255,9 +266,9 @@ __device__ __forceinline__ bool chunk_fwd_step(T* r, T* y, const T* us, bool fir
     from_left<T, RF_FWD>(mine, left, boxL, warp, lane);
     FRec<T> L = first_chunk ? unpack_f(ghostL) : unpack_f(left);
     bool okL = CHECK ? cell_speed_ok(L.us, L.w, k) : true;
-    bool anyvac = L.r < DHTS_EPS;
+    bool anyvac = maybe_vac(L.r);
 #pragma unroll
-    for (int c = 0; c < C; c++) anyvac |= r[c] < DHTS_EPS;
+    for (int c = 0; c < C; c++) anyvac |= maybe_vac(r[c]);
     T f0[2], fpr = T(0), fpy = T(0);
     bool bad;
     if (anyvac) bad = chunk_fwd_sweep<T, C, STORED, CHECK, true>(r, y, us, last, L, k, dt, f0, fpr, fpy, okL);
@@ -276,16 +287,22 @@ __device__ __forceinline__ bool chunk_fwd_step(T* r, T* y, const T* us, bool fir
     return bad;
 }
 
-template <typename T, int C, int MB>
+// NS > 0 (every state stored, K == 1): the state rows go to HBM through an NS-stage shared-memory staging ring and
+// TMA bulk stores issued by one thread -- no per-thread STG, no store address arithmetic, and the state registers
+// are free again as soon as the STS has read them.  NS == 0: per-thread vector stores (sparse checkpoints).
+template <typename T, int C, int MB, int NS>
 __global__ void __launch_bounds__(1024 / (C < 4 ? C : 4), MB) arz_rollout_fwd_reg_kernel(const T* __restrict__ r0, const T* __restrict__ y0,
                                            const T* __restrict__ u0, const T* __restrict__ ghost,
                                            const T* __restrict__ dx, const T* __restrict__ umax_, T dt, int B, int N,
                                            int steps, int K, int lpc, T* __restrict__ ckpt, T* __restrict__ rT,
                                            T* __restrict__ yT, T* __restrict__ uT, int* __restrict__ flags) {
-    extern __shared__ __align__(16) unsigned char raw[];
+    extern __shared__ __align__(128) unsigned char raw[];
     const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5;
     const unsigned lane = threadIdx.x & 31;
     Shm<T> s = carve_shm<T>(raw, lpc, nwarp);
+    const size_t stage_elems = (size_t)2 * lpc * N;
+    T* stg = reinterpret_cast<T*>(raw + ring_offset<T>(lpc, nwarp));     // [NS][2][lpc * N]
+    int stg_i = 0;
     const int tpl = N / C;                        // threads per lane
     const int l = threadIdx.x / tpl, kc = threadIdx.x - l * tpl;
     const int ngroup = (B + lpc - 1) / lpc;
@@ -300,6 +317,7 @@ __global__ void __launch_bounds__(1024 / (C < 4 ? C : 4), MB) arz_rollout_fwd_re
         const LaneK<T> k = s.lk[ll];
         const T* gL = s.ghostF + (ll * 2) * GH_F; const T* gR = gL + GH_F;
         const size_t off = (size_t)(lane0 + ll) * N + (size_t)kc * C;
+        const size_t soff = (size_t)ll * N + (size_t)kc * C;
         const bool first_chunk = kc == 0, last_chunk = kc == tpl - 1;
         const size_t BN = (size_t)B * N;
         T r[C], y[C];
@@ -308,11 +326,24 @@ __global__ void __launch_bounds__(1024 / (C < 4 ? C : 4), MB) arz_rollout_fwd_re
         T* blA = s.boxL; T* blB = s.boxL + nwarp * RF_ADJ;        // double-buffered mailboxes, swapped every step
         T* brA = s.boxR; T* brB = s.boxR + nwarp * 4;
         T* ck = ckpt ? ckpt + off : nullptr;                       // next checkpoint slot of this chunk
+        T* ckrow = ckpt ? ckpt + (size_t)lane0 * N : nullptr;      // same, start of the group's rows (bulk stores)
+        const unsigned rowbytes = (unsigned)((size_t)nl * N * sizeof(T));
         int next_ck = 0;
         for (int t = 0; t < steps; t++) {
-            if (ck && t == next_ck) {
-                if (active) { store_chunk<T, C>(ck, r); store_chunk<T, C>(ck + BN, y); }
-                ck += 2 * BN; next_ck += K;
+            const bool store_now = ck && t == next_ck;
+            if (store_now) {
+                if (NS > 0) {
+                    // Stage t % NS is free: its previous bulk store (step t - NS) was waited for by thread 0 at the
+                    // top of step t - 1, before that step's block barriers.
+                    T* sp = stg + (size_t)stg_i * stage_elems + soff;
+                    if (active) { store_chunk<T, C>(sp, r); store_chunk<T, C>(sp + (size_t)lpc * N, y); }
+                    fence_proxy_async();
+                    if (threadIdx.x == 0) bulk_wait_read<(NS > 2 ? NS - 2 : 0)>();
+                } else {
+                    if (active) { store_chunk<T, C>(ck, r); store_chunk<T, C>(ck + BN, y); }
+                    ck += 2 * BN;
+                }
+                next_ck += K;
             }
             if (t == 0 && u0) {
                 T us[C];
@@ -321,7 +352,19 @@ __global__ void __launch_bounds__(1024 / (C < 4 ? C : 4), MB) arz_rollout_fwd_re
             } else
                 lbad |= chunk_fwd_step<T, C, false, true>(r, y, nullptr, first_chunk, last_chunk, k, gL, gR, dt, blA, brA, warp, nwarp, lane);
             T* x = blA; blA = blB; blB = x; x = brA; brA = brB; brB = x;
+            if (NS > 0 && store_now) {
+                // every thread has passed the step's block barriers: the stage is complete and fenced
+                if (threadIdx.x == 0) {
+                    const T* sp = stg + (size_t)stg_i * stage_elems;
+                    bulk_s2g(ckrow, sp, rowbytes);
+                    bulk_s2g(ckrow + BN, sp + (size_t)lpc * N, rowbytes);
+                    bulk_commit();
+                }
+                ckrow += 2 * BN;
+                if (++stg_i == NS) stg_i = 0;
+            }
         }
+        if (NS > 0 && threadIdx.x == 0) bulk_wait_read<0>();      // stages are rewritten by the next lane group
         bad |= lbad && active;
         if (active) {
             T u[C];
@@ -330,6 +373,7 @@ __global__ void __launch_bounds__(1024 / (C < 4 ? C : 4), MB) arz_rollout_fwd_re
             store_chunk<T, C>(rT + off, r); store_chunk<T, C>(yT + off, y); store_chunk<T, C>(uT + off, u);
         }
     }
+    if (NS > 0 && threadIdx.x == 0) bulk_wait_all();
     if (bad) atomicOr(flags, FLAG_CFL);
 }
 
@@ -379,9 +423,9 @@ __device__ __forceinline__ bool chunk_adj_step(const T* r, const T* y, const T* 
     ARec<T> L = first_chunk ? unpack_a(ghostL) : unpack_a(left);
     T gLr = first_chunk ? T(0) : left[10], gLy = first_chunk ? T(0) : left[11];   // OLD adjoint of the cell on the left
     T a0[2], bpr = T(0), bpy = T(0);
-    bool anyvac = (L.r < DHTS_EPS) || (rl < DHTS_EPS);
+    bool anyvac = maybe_vac(L.r) || maybe_vac(rl);
 #pragma unroll
-    for (int c = 0; c < C - 1; c++) anyvac |= r[c] < DHTS_EPS;
+    for (int c = 0; c < C - 1; c++) anyvac |= maybe_vac(r[c]);
     bool nan;
     if (anyvac) nan = chunk_adj_sweep<T, C, STORED, true>(r, y, us, gr, gy, last, L, gLr, gLy, k, a0, bpr, bpy);
     else nan = chunk_adj_sweep<T, C, STORED, false>(r, y, us, gr, gy, last, L, gLr, gLy, k, a0, bpr, bpy);
@@ -657,9 +701,31 @@ static int rollout_fwd(const T* r0, const T* y0, const T* u0, const T* ghost, co
         return DHTS_ERR_UNSUPPORTED;          // callers step with the tiled kernels instead
     if (K < 1) K = 1;
     int grid = p.grid;
-#define CALL(CC, MB) arz_rollout_fwd_reg_kernel<T, CC, MB><<<grid, p.threads, p.smem, st>>>(r0, y0, u0, ghost, dx, umax, dt, B, N, steps, K, p.lpc, ckpt, rT, yT, uT, flags);
-    DHTS_C_DISPATCH(p, CALL)
+    // every state stored: staging ring + TMA bulk stores when the rows are 16-byte sized and 4 stages fit
+    constexpr int NSF = 4;
+    const size_t stage = (size_t)2 * p.lpc * N * sizeof(T);
+    const size_t base = ring_offset<T>(p.lpc, p.threads / 32);
+    bool staged = ckpt && K == 1 && p.C > 1 && ((size_t)N * sizeof(T)) % 16 == 0 && base + NSF * stage <= 112 * 1024;
+    const char* sg = getenv("DHTS_ARZ_STAGE");                 // tuning knob: 0 = per-thread stores
+    if (sg && atoi(sg) == 0) staged = false;
+    if (staged) {
+        const size_t smem = base + NSF * stage;
+#define CALL(CC, MB)                                                                                                   \
+    {                                                                                                                  \
+        if (smem > 48 * 1024)                                                                                          \
+            cudaFuncSetAttribute(arz_rollout_fwd_reg_kernel<T, CC, MB, NSF>,                                           \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                              \
+        arz_rollout_fwd_reg_kernel<T, CC, MB, NSF><<<grid, p.threads, smem, st>>>(r0, y0, u0, ghost, dx, umax, dt, B,  \
+                                                                                  N, steps, K, p.lpc, ckpt, rT, yT,    \
+                                                                                  uT, flags);                          \
+    }
+        DHTS_C_DISPATCH(p, CALL)
 #undef CALL
+    } else {
+#define CALL(CC, MB) arz_rollout_fwd_reg_kernel<T, CC, MB, 0><<<grid, p.threads, p.smem, st>>>(r0, y0, u0, ghost, dx, umax, dt, B, N, steps, K, p.lpc, ckpt, rT, yT, uT, flags);
+        DHTS_C_DISPATCH(p, CALL)
+#undef CALL
+    }
     return status_r();
 }
 

@@ -52,6 +52,12 @@ template <typename T> __device__ __forceinline__ LaneK<T> make_lanek(T umax, T d
     return k;
 }
 
+// Conservative "may be below eps" test on the integer pipe (the high word of a double orders like the value; a
+// tie with the high word of eps counts as "maybe").  Used only to choose between the general sweep and the
+// vacuum-free one, so a false positive costs time, never correctness.
+__device__ __forceinline__ bool maybe_vac(double r) { return __double2hiint(r) <= 0x3EE4F8B5; }   // 1e-5 = 0x3EE4F8B5'88E368F1
+__device__ __forceinline__ bool maybe_vac(float r) { return __float_as_int(r) <= __float_as_int(1e-5f); }
+
 // ---------------------------------------------------------------------------- forward
 constexpr int RF_FWD = 6;
 template <typename T> struct FRec { T r, us, sq, w, fr, fy; };   // fr, fy: flux if this cell is the Q_L outcome

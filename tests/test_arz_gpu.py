@@ -151,21 +151,25 @@ def test_rollout_vs_oracle_shapes(dev, B, N, T, K):
 
 
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
-def test_rollout_ring_equals_register_prefetch(dev, dtype):
-    """Every-state-stored adjoint: the TMA ring variant (state rows staged in shared memory by cp.async.bulk) and the
-    register-prefetch variant do the same arithmetic, so gradients must agree to rounding (observed: bitwise or 1 ulp) -- persistent loop over
-    more lane groups than CTAs, ragged last group, fewer steps than ring stages, stored-speed first step."""
+def test_rollout_tma_paths_equal_plain_paths(dev, dtype):
+    """Every state stored: the forward's staged TMA bulk stores (shared-memory staging ring, cp.async.bulk to HBM) and
+    the adjoint's TMA state ring (cp.async.bulk into shared memory, mbarrier completion) against the per-thread
+    store / register-prefetch variants.  Same arithmetic, so gradients must agree to rounding (observed: bitwise
+    or 1 ulp) -- persistent loop over more lane groups than CTAs, ragged last group, fewer steps than ring
+    stages, stored-speed first step."""
     import os
     import dhts_b200
     from dhts_b200 import functional as F
     rng = np.random.default_rng(5)
+    variants = {"tma": {}, "ring2": {"DHTS_ARZ_RING": "2"}, "plain_adj": {"DHTS_ARZ_RING": "0"},
+                "plain": {"DHTS_ARZ_RING": "0", "DHTS_ARZ_STAGE": "0"}}
     for B, N, T in ((701, 1024, 7), (301, 64, 9), (9, 256, 2), (40, 2048, 5)):
         r0 = rng.uniform(0, 1, (B, N)); u0 = rng.uniform(0, 30, (B, N))
         gr = rng.uniform(0, 1, (B, 2)); gu = rng.uniform(0, 30, (B, 2)); w = rng.normal(size=(B, N))
         t = lambda a: torch.tensor(a, dtype=dtype, device=dev)
         out = {}
-        for ring in ("4", "2", "0"):
-            os.environ["DHTS_ARZ_RING"] = ring
+        for name, env in variants.items():
+            os.environ.update(env)
             try:
                 flags = dhts_b200.Flags(dev)
                 tr, tu = t(r0).requires_grad_(), t(u0).requires_grad_()
@@ -173,13 +177,14 @@ def test_rollout_ring_equals_register_prefetch(dev, dtype):
                 rT, yT, uT = F.arz_rollout(tr, tu, tgr, tgu, 5.0, 30.0, 0.01, T, ckpt_every=1, flags=flags)
                 ((rT * t(w)).sum() + (uT * t(w / 30)).sum()).backward()
                 flags.check()
-                out[ring] = [x.clone() for x in (tr.grad, tu.grad, tgr.grad, tgu.grad)]
+                out[name] = [x.clone() for x in (rT.detach(), uT.detach(), tr.grad, tu.grad, tgr.grad, tgu.grad)]
             finally:
-                del os.environ["DHTS_ARZ_RING"]
+                for k in env:
+                    del os.environ[k]
         tol = 1e-13 if dtype == torch.float64 else 1e-5       # same arithmetic; the compiler may contract differently
-        for ring in ("4", "2"):
-            for a, b in zip(out[ring], out["0"]):
-                assert relerr(a.cpu(), b.cpu()) < tol, (B, N, T, ring)
+        for name in ("tma", "ring2", "plain_adj"):
+            for a, b in zip(out[name], out["plain"]):
+                assert relerr(a.cpu(), b.cpu()) < tol, (B, N, T, name)
 
 
 def test_rollout_equals_chained_steps(dev):
