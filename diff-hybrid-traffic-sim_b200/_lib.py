@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libdhts_b200.so")
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, 1, 2, 3
-FLAG_CFL, FLAG_NAN_GRAD, FLAG_COLLISION = 1, 2, 4
+FLAG_CFL, FLAG_NAN_GRAD, FLAG_COLLISION, FLAG_ROUTE = 1, 2, 4, 8
 _ERR = {ERR_INVALID: "invalid argument", ERR_UNSUPPORTED: "unsupported shape for the fused kernel",
         ERR_CUDA: "CUDA launch failed"}
 
@@ -25,7 +25,7 @@ SYMBOLS = [
 ] + [f"dhts_{op}_{suf}" for suf in ("f64", "f32") for op in (
     "arz_step_fwd", "arz_step_bwd", "arz_rollout_fwd", "arz_rollout_scratch_elems", "arz_rollout_bwd",
     "idm_step_fwd", "idm_step_bwd", "idm_rollout_fwd", "idm_rollout_bwd",
-    "m2c_fwd", "m2c_bwd", "c2m_fwd", "c2m_bwd")]
+    "m2c_fwd", "m2c_bwd", "c2m_fwd", "c2m_bwd", "net_rollout_fwd", "net_rollout_bwd")]
 
 _lib = None
 
@@ -112,6 +112,9 @@ class Flags:
         assert not (bits & FLAG_CFL), "Time step size does not meet CFL condition. Please try smaller delta_time."
         # road/lane/dmacro_lane.py:308
         assert not (bits & FLAG_NAN_GRAD), ""
+        if bits & FLAG_ROUTE:
+            # road/network/road_network.py:332-339: self.lane[-1] when the step's MacroRoute selects no neighbour
+            raise KeyError(-1)
         if (bits & FLAG_COLLISION) and not quiet_collisions:
             # road/lane/_micro_lane.py:155-160 prints and continues
             print("Collision detected (%d vehicle-steps)" % ncol)

@@ -220,6 +220,75 @@ int dhts_c2m_bwd_f32(const float* p_head, const float* v_head, const float* a_he
                      const float* g_u_out, float* g_p, float* g_v, float* g_a, float* g_r, float* g_y, float* g_u,
                      void* stream);
 
+/* ---------------------------------------------------------------- connected macro network, fused T-step rollout
+ * Steps R independent replicas of ONE connected network of macro lanes for `steps` steps in a single launch
+ * (one CTA per replica, network state in shared memory), forward and adjoint.  Per step and replica it stands for
+ *   RoadNetwork.forward                      road/network/road_network.py:79-111   (Jacobi: boundaries, forward, update)
+ *   RoadNetwork.get_macro_boundary           road/network/road_network.py:299-362
+ *   ItscpRoadNetwork.setup_macro_boundary    example/control/itscp/_simulator.py:56-142      (mode 1)
+ *   set_leftmost_cell / set_rightmost_cell   road/lane/_macro_lane.py:156-162 (FullQ.from_r_u, model/macro/_arz.py:74-80)
+ *   dMacroLane.forward + dMacroForwardLayer  road/lane/dmacro_lane.py:68-132,234-310
+ *   the queue-length reward (optional)       example/control/itscp/_env.py:662-742,770-797
+ * and for the autograd chain through them.
+ *
+ * Topology (device arrays shared by all replicas; side 0 = predecessors / left ghost, 1 = successors / right ghost):
+ *   cell_off [L+1]   CSR of the cells, lane by lane (NC = cell_off[L])
+ *   nadj     [2][L]  number of adjacent lanes per side
+ *   one_adj  [2][L]  the adjacent lane when there is exactly one, else -1
+ *   adj_off  [2][L+1], adj [E]  adjacency lists (absolute offsets into adj)
+ *   own_slot [2][L]  slot (0..n_own-1) of the lane's own ghost record for sides that can feed on it, else -1
+ * Per call:
+ *   dx [L] cell length per lane;  umax, dt, veh_len, static_speed scalars of the network
+ *   route [Rr][steps][2][L] int32 or NULL: (prev lane, next lane) chosen by the MacroRoute of each step, -1 = none;
+ *                    Rr = R when route_per_replica, else 1
+ *   mode 0: ghost = source (plain RoadNetwork); mode 1: ITSCP signal blend with
+ *   sig, incoming [R][steps][L]: lane_signal / lane_incoming of each step; soft = 1: sigmoid(32(sig-0.5)) on the right
+ *                    side (differentiable=True), 0: sig > 0.5
+ *   qk [steps] or NULL: sigmoid constant of the queue reward per step; reward [R] = -sum_t sum_lanes q^2 dt
+ *   r0, y0, u0 [R][NC]; own0 [R][n_own][2] initial (r, u) of the own ghost records
+ *   hist [steps+1][R][3][NC]  every state (r, y, u): before step t, and after the last step (output, kept for bwd)
+ *   own_hist [steps+1][R][n_own][2]
+ * Backward:
+ *   g_states [steps][R][3][NC] or NULL  dLoss/d(r, y, u) of the state AFTER step t (last = terminal adjoint)
+ *   g_reward [R] or NULL                dLoss/d reward (needs qk)
+ *   g_r0, g_y0, g_u0 [R][NC]; g_own0 [R][n_own][2] or NULL; g_sig, g_incoming [R][steps][L] or NULL
+ * Flags: DHTS_FLAG_CFL, DHTS_FLAG_NAN_GRAD, DHTS_FLAG_ROUTE (a lane with several neighbours on one side has none
+ * selected by the step's route; the reference raises KeyError there).
+ */
+#define DHTS_FLAG_ROUTE 8
+typedef struct dhts_net_topology {
+    int L, NC, n_own;
+    const int* cell_off;
+    const int* nadj;
+    const int* one_adj;
+    const int* adj_off;
+    const int* adj;
+    const int* own_slot;
+} dhts_net_topology;
+
+int dhts_net_rollout_fwd_f64(const dhts_net_topology* topo, const double* dx, const int* route, int route_per_replica,
+                             const double* sig, const double* incoming, const double* qk, double umax, double dt,
+                             double veh_len, double static_speed, int steps, int R, int mode, int soft,
+                             const double* r0, const double* y0, const double* u0, const double* own0, double* hist,
+                             double* own_hist, double* reward, int* flags, void* stream);
+int dhts_net_rollout_fwd_f32(const dhts_net_topology* topo, const float* dx, const int* route, int route_per_replica,
+                             const float* sig, const float* incoming, const float* qk, float umax, float dt,
+                             float veh_len, float static_speed, int steps, int R, int mode, int soft, const float* r0,
+                             const float* y0, const float* u0, const float* own0, float* hist, float* own_hist,
+                             float* reward, int* flags, void* stream);
+int dhts_net_rollout_bwd_f64(const dhts_net_topology* topo, const double* dx, const int* route, int route_per_replica,
+                             const double* sig, const double* incoming, const double* qk, double umax, double dt,
+                             double veh_len, double static_speed, int steps, int R, int mode, int soft,
+                             const double* hist, const double* own_hist, const double* g_states,
+                             const double* g_reward, double* g_r0, double* g_y0, double* g_u0, double* g_own0,
+                             double* g_sig, double* g_incoming, int* flags, void* stream);
+int dhts_net_rollout_bwd_f32(const dhts_net_topology* topo, const float* dx, const int* route, int route_per_replica,
+                             const float* sig, const float* incoming, const float* qk, float umax, float dt,
+                             float veh_len, float static_speed, int steps, int R, int mode, int soft,
+                             const float* hist, const float* own_hist, const float* g_states, const float* g_reward,
+                             float* g_r0, float* g_y0, float* g_u0, float* g_own0, float* g_sig, float* g_incoming,
+                             int* flags, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
