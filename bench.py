@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--idm-ckpt-every", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-net", action="store_true", help="skip the secondary connected-network (ITSCP) measurement")
+    ap.add_argument("--net-replicas", type=int, default=2048)
     return ap.parse_args()
 
 
@@ -200,6 +202,64 @@ def run_reference(a):
             "e2e": {"value": va, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.time() - t0}
     print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------- connected network (secondary)
+
+def network_bench(a, dev, dt_t, torch):
+    """Secondary measurement: BASELINE.json configs[3]'s lane graph in macro mode -- 3 x 3 intersections,
+    1 lane per road, 5 m access lanes (144 lanes, 288 cells), u_max 60, 30 Hz, 600 frames, 4 s signals -- rolled out
+    for `net_replicas` candidate signal plans at once, forward + adjoint (gradient of the fused queue reward wrt
+    every action), through dhts_net_rollout_{fwd,bwd}."""
+    import numpy as np
+    from dhts_b200.itscp import ItscpBatch, ItscpGrid
+    grid = ItscpGrid(3, 1, 5.0, 5.0)
+    env = ItscpBatch(grid, dev, speed_limit=60.0, simulation_frequency=30, signal_length=4.0, dtype=dt_t)
+    R, T, L, NC = a.net_replicas, 600, grid.L, env.topo.NC
+    rng = np.random.default_rng(SEED)
+    nxt, route = env.topo.next, -np.ones((T, 2, L), dtype=np.int32)
+    for t in range(T):          # RoadNetwork.create_random_macro_route (road_network.py:389-423)
+        for l in rng.permutation(L):
+            for n in (rng.permutation(nxt[l]) if nxt[l] else []):
+                if route[t, 0, n] < 0:
+                    route[t, 1, l] = n; route[t, 0, n] = l
+                    break
+    g = torch.Generator().manual_seed(SEED + 31)
+    n_act = (T // env.frames_per_signal) * 9
+    action = (0.1 + 0.8 * torch.rand((R, n_act), generator=g, dtype=torch.float32)).to(dt_t).to(dev).requires_grad_()
+    sess = torch.rand((R, 5, L), generator=g, dtype=torch.float32).to(dt_t)          # itscp_random_schedule: 5 sessions
+    incoming = sess.repeat_interleave(T // 5, dim=1).contiguous().to(dev)
+    route_t = torch.tensor(route, device=dev)
+    qk = torch.full((T,), 16.0 / 30.0, dtype=dt_t, device=dev)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    fwd_ms, bwd_ms = [], []
+    for it in range(3):
+        action.grad = None
+        e = [ev() for _ in range(4)]
+        sig = grid.signals(action, T, env.frames_per_signal, soft=True)
+        e[0].record()
+        reward, states = env.rollout(action, incoming, route_t, T, differentiable=True, exact_constants=False, qk=qk)
+        e[1].record()
+        loss = reward.sum()
+        e[2].record()
+        loss.backward()
+        e[3].record()
+        torch.cuda.synchronize()
+        if it:
+            fwd_ms.append(e[0].elapsed_time(e[1])); bwd_ms.append(e[2].elapsed_time(e[3]))
+        del states, reward, loss, sig
+    f, b = sum(fwd_ms) / len(fwd_ms), sum(bwd_ms) / len(bwd_ms)
+    upd = R * NC * T
+    esz = 8 if dt_t == torch.float64 else 4
+    return {"workload": "ITSCP 3x3 grid, macro mode: %d lanes / %d cells per replica, %d replicas, %d frames fwd+bwd "
+                        "(signals from %d actions per replica, fused queue reward)" % (L, NC, R, T, n_act),
+            "value": upd / ((f + b) / 1e3), "unit": "cell-updates/s", "fwd_ms": f, "bwd_ms": b,
+            "replica_rollouts_per_s": R / ((f + b) / 1e3),
+            "stored_state_bytes": (T + 1) * R * 3 * NC * esz, "gpu_launches": 2,
+            "mean_reward": float(env.rollout(action.detach(), incoming, route_t, T, exact_constants=False, qk=qk)[0].mean()),
+            "grad_abs_mean": float(action.grad.abs().mean()),
+            "reference_note": "the reference steps this network lane by lane in Python: ~2.5-4.3e3 cell-updates/s per "
+                              "core (BASELINE.md sec. 2), i.e. ~40-70 s per 600-frame episode fwd+bwd"}
 
 
 # ----------------------------------------------------------------------------------------- our arm
@@ -446,6 +506,10 @@ def run_ours(a):
                            "note": "whole pass (ARZ + IDM) from pinned host buffers, gradients and losses read back, copies "
                                    "pipelined with the compute per lane chunk; value counts ARZ cell-updates over the "
                                    "WHOLE pass time (IDM and copies included)"}
+        if not a.no_net:
+            del arz_arena, devA, devM
+            torch.cuda.empty_cache()
+            line["itscp_net"] = network_bench(a, dev, dt_t, torch)
         if not a.no_cpu_baseline:
             ra, ri, cores, sample = cpu_port_rates(a)
             line["cpu_baseline"] = {"value": ra, "unit": "cell-updates/s", "cores": cores, "kind": "port",
