@@ -12,7 +12,7 @@ from ._lib import Flags, UnsupportedShape  # noqa: F401
 
 def __getattr__(name):
     # torch-facing modules are imported lazily so that `build()` works before the .so exists
-    if name in ("ops", "functional", "dist", "dropin", "network", "itscp"):
+    if name in ("ops", "functional", "dist", "dropin", "network", "itscp", "hybrid_network"):
         import importlib
         return importlib.import_module(__name__ + "." + name)
     raise AttributeError(name)

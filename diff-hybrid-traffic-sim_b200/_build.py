@@ -8,7 +8,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 SO = os.path.join(_HERE, "libdhts_b200.so")
-SOURCES = ["arz_kernels.cu", "arz_rollout.cu", "idm_kernels.cu", "convert_kernels.cu", "net_kernels.cu", "capi_misc.cu"]
+SOURCES = ["arz_kernels.cu", "arz_rollout.cu", "idm_kernels.cu", "convert_kernels.cu", "net_kernels.cu", "net_hybrid.cu", "capi_misc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-fvisibility=hidden"]
 

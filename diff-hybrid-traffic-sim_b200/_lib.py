@@ -15,17 +15,17 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libdhts_b200.so")
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, 1, 2, 3
-FLAG_CFL, FLAG_NAN_GRAD, FLAG_COLLISION, FLAG_ROUTE = 1, 2, 4, 8
+FLAG_CFL, FLAG_NAN_GRAD, FLAG_COLLISION, FLAG_ROUTE, FLAG_VEH_OVERFLOW = 1, 2, 4, 8, 16
 _ERR = {ERR_INVALID: "invalid argument", ERR_UNSUPPORTED: "unsupported shape for the fused kernel",
         ERR_CUDA: "CUDA launch failed"}
 
 # every exported symbol of include/dhts.h; tests/test_cabi.py checks this list against the header
 SYMBOLS = [
-    "dhts_version", "dhts_csr_expand", "dhts_idm_rollout_max_lane", "dhts_idm_rollout_max_ckpt_every",
+    "dhts_version", "dhts_csr_expand", "dhts_idm_rollout_max_lane", "dhts_idm_rollout_max_ckpt_every", "dhts_hyb_aux_size",
 ] + [f"dhts_{op}_{suf}" for suf in ("f64", "f32") for op in (
     "arz_step_fwd", "arz_step_bwd", "arz_rollout_fwd", "arz_rollout_scratch_elems", "arz_rollout_bwd",
     "idm_step_fwd", "idm_step_bwd", "idm_rollout_fwd", "idm_rollout_bwd",
-    "m2c_fwd", "m2c_bwd", "c2m_fwd", "c2m_bwd", "net_rollout_fwd", "net_rollout_bwd")]
+    "m2c_fwd", "m2c_bwd", "c2m_fwd", "c2m_bwd", "net_rollout_fwd", "net_rollout_bwd", "hyb_rollout_fwd", "hyb_rollout_bwd")]
 
 _lib = None
 
@@ -112,6 +112,9 @@ class Flags:
         assert not (bits & FLAG_CFL), "Time step size does not meet CFL condition. Please try smaller delta_time."
         # road/lane/dmacro_lane.py:308
         assert not (bits & FLAG_NAN_GRAD), ""
+        if bits & FLAG_VEH_OVERFLOW:
+            raise RuntimeError("hybrid network rollout: a vehicle ring, spawn-route list or deposit log overflowed "
+                               "(raise veh_cap / max_spawn)")
         if bits & FLAG_ROUTE:
             # road/network/road_network.py:332-339: self.lane[-1] when the step's MacroRoute selects no neighbour
             raise KeyError(-1)

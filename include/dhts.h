@@ -289,6 +289,82 @@ int dhts_net_rollout_bwd_f32(const dhts_net_topology* topo, const float* dx, con
                              float* g_r0, float* g_y0, float* g_u0, float* g_own0, float* g_sig, float* g_incoming,
                              int* flags, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Connected HYBRID network rollout (macro ARZ lanes + micro IDM lanes + the conversions between them), one CTA per
+ * replica, forward and adjoint: configs 3 and 4 (hybrid inverse problem, ITSCP hybrid mode) in one launch.  Per step
+ * and replica it stands for everything dhts_net_rollout_* does plus
+ *   RoadNetwork.setup_micro_boundary        road/network/road_network.py:429-580   leader of a head vehicle along its route
+ *   ItscpRoadNetwork.setup_micro_boundary   example/control/itscp/_simulator.py:144-276  signal-blended head deltas (mode 1)
+ *   dMicroLane.forward + dMicroForwardLayer road/lane/dmicro_lane.py:87-153,228-297
+ *   RoadNetwork.conversion / Conversion.*   road/network/road_network.py:113-173, road/network/conversion.py:15-215
+ * and for the autograd chain through them.
+ *
+ * Topology (device arrays): the dhts_net_topology fields (micro lanes have no cells: cell_off[l+1] == cell_off[l]) and
+ *   kind [L] 0 macro / 1 micro;  mic_of [L] micro index or -1;  mic_lane [ML] lane id of a micro index
+ *   cap_off [L+1], cap_lane [NCAP]  flux capacitors of a macro lane: one per micro successor (MacroLane.flux_capacitor)
+ *   grp_off [NG+1], grp_lane [NGL]  conversion groups: lanes that take part in conversions, partitioned into connected
+ *                    components of "may touch the same lane", ascending lane id inside a group
+ *   routes [NR][RLEN] lane ids along a vehicle route (MicroRoute.route), -1 terminated
+ *   cap   vehicle slots per micro lane;  MAXT  max cells one absorbed vehicle can overlap (ceil(len / min dx) + 1)
+ * Per call (beyond dhts_net_rollout_*):
+ *   lane_len [L];  veh_par [6] HOST array (a_max, a_pref, v_target, s0, T, length) of every vehicle
+ *   spawn_route [Rs][ML][KS] int32: route id of the k-th vehicle spawned into a micro lane (Rs = R or 1)
+ *   aux0 [R][AUX] (AUX = dhts_hyb_aux_size): vehicles p, v, a, route id, route cursor, each [ML][cap] by ring slot;
+ *                    ring front, count, spawn counter [ML]; capacitors [NCAP]; running-mean (sum, count) of the micro
+ *                    signal (_simulator.py:255-262); integers stored as reals
+ *   hist [steps+1][R][4][NC] (r, y, u, stored u_eq);  own_hist;  aux_hist [steps+1][R][AUX];
+ *   head_hist [steps][R][ML][2] or NULL: head deltas each micro lane used
+ * Backward: g_states [steps][R][4][NC] or NULL;  g_aux [steps][R][AUX] or NULL (p, v, a entries of the vehicles that
+ *   exist after step t are read);  g_aux0 [R][AUX] or NULL (p, v, a of the initial vehicles and the capacitors).
+ * Flags: as dhts_net_rollout_* plus DHTS_FLAG_COLLISION and DHTS_FLAG_VEH_OVERFLOW (ring, spawn-route list or MAXT
+ * exhausted: raise cap / KS).
+ */
+#define DHTS_FLAG_VEH_OVERFLOW 16
+typedef struct dhts_hyb_topology {
+    int L, NC, n_own;
+    const int* cell_off;
+    const int* nadj;
+    const int* one_adj;
+    const int* adj_off;
+    const int* adj;
+    const int* own_slot;
+    int ML, cap, NCAP, NG, NGL, NR, RLEN, MAXT;
+    const int* kind;
+    const int* mic_of;
+    const int* mic_lane;
+    const int* cap_off;
+    const int* cap_lane;
+    const int* grp_off;
+    const int* grp_lane;
+    const int* routes;
+} dhts_hyb_topology;
+
+int dhts_hyb_aux_size(const dhts_hyb_topology* topo);
+int dhts_hyb_rollout_fwd_f64(const dhts_hyb_topology* topo, const double* dx, const double* lane_len, const int* route,
+                             int route_per_replica, const int* spawn_route, int spawn_per_replica, int KS,
+                             const double* sig, const double* incoming, const double* veh_par, double umax, double dt, int steps,
+                             int R, int mode, int soft, const double* r0, const double* y0, const double* u0, const double* own0,
+                             const double* aux0, double* hist, double* own_hist, double* aux_hist, double* head_hist, int* flags,
+                             void* stream);
+int dhts_hyb_rollout_bwd_f64(const dhts_hyb_topology* topo, const double* dx, const double* lane_len, const int* route,
+                             int route_per_replica, const int* spawn_route, int spawn_per_replica, int KS,
+                             const double* sig, const double* incoming, const double* veh_par, double umax, double dt, int steps,
+                             int R, int mode, int soft, const double* hist, const double* own_hist, const double* aux_hist,
+                             const double* g_states, const double* g_aux, double* g_r0, double* g_y0, double* g_u0, double* g_own0,
+                             double* g_sig, double* g_incoming, double* g_aux0, int* flags, void* stream);
+int dhts_hyb_rollout_fwd_f32(const dhts_hyb_topology* topo, const float* dx, const float* lane_len, const int* route,
+                             int route_per_replica, const int* spawn_route, int spawn_per_replica, int KS,
+                             const float* sig, const float* incoming, const float* veh_par, float umax, float dt, int steps,
+                             int R, int mode, int soft, const float* r0, const float* y0, const float* u0, const float* own0,
+                             const float* aux0, float* hist, float* own_hist, float* aux_hist, float* head_hist, int* flags,
+                             void* stream);
+int dhts_hyb_rollout_bwd_f32(const dhts_hyb_topology* topo, const float* dx, const float* lane_len, const int* route,
+                             int route_per_replica, const int* spawn_route, int spawn_per_replica, int KS,
+                             const float* sig, const float* incoming, const float* veh_par, float umax, float dt, int steps,
+                             int R, int mode, int soft, const float* hist, const float* own_hist, const float* aux_hist,
+                             const float* g_states, const float* g_aux, float* g_r0, float* g_y0, float* g_u0, float* g_own0,
+                             float* g_sig, float* g_incoming, float* g_aux0, int* flags, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
