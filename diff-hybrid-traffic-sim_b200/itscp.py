@@ -27,7 +27,7 @@ from .network import MODE_ITSCP, MacroNetTopology, net_rollout
 LANE_WIDTH = 4.0          # highway_env AbstractLane.DEFAULT_WIDTH, _env.py:233
 
 
-@dataclass
+@dataclass(eq=False)     # identity hash: schedule callbacks key dicts by lane id objects (_env.py:23-60)
 class LaneInfo:
     row: int
     col: int

@@ -36,7 +36,8 @@ CAP = 4          # vehicles recorded per micro lane (asserted below)
 RLEN = 32        # MAX_ROUTE_LENGTH, road_network.py:15
 
 
-def run_case(tag, grid, T, frames_per_signal, seed, umax=60.0, freq=30, static_speed=0.2, inflow=(0.2, 0.9)):
+def run_case(tag, grid, T, frames_per_signal, seed, umax=60.0, freq=30, static_speed=0.2, inflow=(0.2, 0.9), empty=False,
+             schedule=None, action_range=(0.1, 0.9)):
     from dmath.operation import sigmoid
     from road.lane.dmacro_lane import dMacroLane
     from road.lane.dmicro_lane import dMicroLane
@@ -72,18 +73,25 @@ def run_case(tag, grid, T, frames_per_signal, seed, umax=60.0, freq=30, static_s
     NC = int(off[-1])
     n2 = n * n
     n_phase = max(1, T // frames_per_signal)
-    action = th.tensor(rng.uniform(0.1, 0.9, n_phase * n2), requires_grad=True)
+    action = th.tensor(rng.uniform(action_range[0], action_range[1], n_phase * n2), requires_grad=True)
     bl = grid.boundary_lanes()
     assert all(kind[l] == 0 for l in bl)
     inc_np = np.zeros((T, L))
-    for l in bl:
-        for s0 in range(0, T, max(1, T // 5)):
-            inc_np[s0:s0 + max(1, T // 5), l] = rng.uniform(*inflow)
+    if schedule is not None:      # an _env.py schedule callback restated by the caller (lane infos, T) -> [T, L]
+        full = schedule(grid.lanes, T)
+        for l in bl:
+            inc_np[:, l] = full[:, l]
+    else:
+        for l in bl:
+            for s0 in range(0, T, max(1, T // 5)):
+                inc_np[s0:s0 + max(1, T // 5), l] = rng.uniform(*inflow)
     inc = {(t, l): th.tensor(inc_np[t, l], requires_grad=True) for t in range(T) for l in bl}
     routes = [net.create_random_macro_route() for _ in range(T)]       # macro_route_schedule, _env.py:194-200
     route_tab = np.array([[[r.get_prev_lane(l) for l in range(L)], [r.get_next_lane(l) for l in range(L)]] for r in routes],
                          dtype=np.int32)
     r0_np = rng.uniform(0.1, 0.8, NC); u0_np = rng.uniform(0.3, 1.0, NC) * umax * (1.0 - 0.7 * r0_np)
+    if empty:                     # lanes as _make_lane leaves them: ARZ.FullQ(u_max), model/macro/_arz.py:59-63
+        r0_np = np.zeros(NC); u0_np = np.full(NC, umax)
     r0 = th.tensor(r0_np, requires_grad=True); u0 = th.tensor(u0_np, requires_grad=True)
     for l in range(L):
         if not kind[l]:

@@ -115,3 +115,49 @@ def test_hybrid_collisions_and_nan_gradients_are_flagged(dev):
     if not finite:
         with pytest.raises(AssertionError):
             flags.check(quiet_collisions=True)
+
+
+def test_plain_mode_chain_matches_live_reference(dev):
+    """MODE_PLAIN (no signals): the macro(10) -> micro -> macro(10) chain of SURVEY A.5 / config 3 through the FUSED
+    hybrid rollout against tests/golden/hybrid_chain_fp64.npz (live reference, 700 steps, 19 spawns, 12 absorptions):
+    spawn / on-lane counts and capacitor per step, final cells and vehicles, loss, gradients reaching lane 0 from a loss
+    on lane 2."""
+    from conftest import golden
+    from dhts_b200 import Flags
+    from dhts_b200.hybrid_network import HybridNetTopology, hybrid_rollout
+    from dhts_b200.network import MODE_PLAIN
+    g = golden("hybrid_chain_fp64")
+    N, dx, umax, dt, T = int(g["N"]), float(g["dx"]), float(g["umax"]), float(g["dt"]), int(g["T"])
+    topo = HybridNetTopology([0, 1, 0], [N, 0, N], [dx, 1.0, dx], [N * dx] * 3, [(0, 1), (1, 2)], dev, MODE_PLAIN, veh_cap=12)
+    assert topo.n_own == 4 and topo.NCAP == 1 and topo.routes == [(1, 2)]
+    gh = g["ghost_ru"]
+    own0 = t64(np.stack([gh[0], gh[2], gh[1], gh[3]])[None], dev)        # own slots: (left l0, left l2, right l0, right l2)
+    r0 = t64(g["r0"].reshape(1, -1), dev, True); u0 = t64(g["u0"].reshape(1, -1), dev, True)
+    route = torch.tensor([[[-1, 0, -1], [1, -1, -1]]] * T, dtype=torch.int32, device=dev)     # create_random_macro_route: 0 -> 1 only
+    sp = torch.zeros((1, 32), dtype=torch.int32, device=dev)
+    flags = Flags(dev)
+    st = hybrid_rollout(topo, r0, u0, umax, dt, T, route=route, spawn_route=sp, own0=own0, flags=flags)
+    flags.check()
+    cnt = st.count[1:, 0, 0].cpu().numpy()
+    assert (cnt == g["nveh_hist"]).all()
+    nsp = st.aux[1:, 0, topo.A_NSP].detach().round().long().cpu().numpy()
+    assert (nsp == g["nspawn_hist"]).all() and nsp[-1] == 19
+    assert np.abs(st.capacitor[1:, 0, 0].detach().cpu().numpy() - g["cap_hist"]).max() < 1e-9
+    cells = st.cells[T, 0].detach().cpu().numpy()                          # [3, 20]
+    assert np.abs(cells[:, :N] - g["lane0"]).max() < 1e-9 and np.abs(cells[:, N:] - g["lane2"]).max() < 1e-9
+    p, v, a, valid = st.by_rank()
+    n = int(cnt[-1])
+    tail_first = lambda x: torch.flip(x[T, 0, 0, :n], dims=[0])
+    veh = torch.stack([tail_first(p), tail_first(v), tail_first(a)], -1)
+    assert veh.shape == g["veh"].shape and np.abs(veh.detach().cpu().numpy() - g["veh"]).max() < 1e-9
+    loss = (st.cells[T, 0, 0, N:] * t64(g["w_r"], dev)).sum() + (st.cells[T, 0, 2, N:] * t64(g["w_u"], dev)).sum()
+    w = g["w_veh"]
+    for i in range(n):
+        loss = loss + float(w[2 * i % 8]) * veh[i, 0] * 0.01 + float(w[(2 * i + 1) % 8]) * veh[i, 1] * 0.01
+    assert abs(float(loss) - float(g["loss"])) < 1e-9
+    loss.backward()
+    flags.check()
+    gr, gu = r0.grad[0].cpu().numpy(), u0.grad[0].cpu().numpy()
+    assert relerr(gr[:N], g["g_r0_lane0"]) < 1e-8 and relerr(gu[:N], g["g_u0_lane0"]) < 1e-8
+    assert relerr(gr[N:], g["g_r0_lane2"]) < 1e-8 and relerr(gu[N:], g["g_u0_lane2"]) < 1e-8
+    assert np.abs(g["g_r0_lane0"]).max() > 0
