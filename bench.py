@@ -262,6 +262,46 @@ def network_bench(a, dev, dt_t, torch):
                               "core (BASELINE.md sec. 2), i.e. ~40-70 s per 600-frame episode fwd+bwd"}
 
 
+def config4_bench(a, dev, dt_t, torch):
+    """Secondary measurement: BASELINE.json configs[3] itself -- one training episode of run_itscp_hybrid.sh (hybrid mode,
+    3 x 3 intersections, centre intersection micro, 600 frames, 45 actions, problem_1 inflow) through the headless env:
+    action -> signals -> fused hybrid rollout -> queue reward with running-mean constants -> gradient wrt the actions.
+    R = 1 is what the reference's trainer does per epoch (trainer.py:140-162 with 1 episode); R = 256 batches episodes."""
+    import numpy as np
+    from dhts_b200.itscp_env import ItscpEnv, problem_1
+    np.random.seed(SEED)
+    env = ItscpEnv(device=dev, dtype=dt_t)
+    env.schedule_callback = problem_1
+    env.config.update(num_intersection=3, lane_length=5.0, num_lane=1, policy_length=20, signal_length=4, mode="hybrid",
+                      speed_limit=60.0)
+    env.reset()
+    g = torch.Generator().manual_seed(SEED + 41)
+    out = {"workload": "run_itscp_hybrid.sh episode: 144 lanes (128 macro / 16 micro), 600 frames fwd+bwd, exact running-mean "
+                       "queue reward, gradient wrt 45 actions"}
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    for R in (1, 256):
+        action = (0.3 + 0.4 * torch.rand((R, env.action_size()), generator=g, dtype=torch.float32)).to(dt_t).to(dev).requires_grad_()
+        env.resample_spawn_routes(R, g)
+        ms = []
+        for it in range(3):
+            action.grad = None
+            e0, e1 = ev(), ev()
+            e0.record()
+            reward = env.rollout(action, True)
+            reward.sum().backward()
+            e1.record()
+            torch.cuda.synchronize()
+            if it:
+                ms.append(e0.elapsed_time(e1))
+        bits, ncol = env.flags.read()
+        out["R%d" % R] = {"ms_per_batch": sum(ms) / len(ms), "episodes_per_s": R / (sum(ms) / len(ms) / 1e3),
+                          "mean_reward": float(reward.mean()), "grad_abs_mean": float(action.grad.abs().mean()),
+                          "flag_bits": bits, "collision_steps": ncol}
+    out["reference_note"] = ("the live reference needs ~200 s for the same episode forward + backward on one host core "
+                             "(oracle/gen_golden_c4.py in the build container; it is single-threaded Python)")
+    return out
+
+
 # ----------------------------------------------------------------------------------------- our arm
 
 def run_ours(a):
@@ -510,6 +550,8 @@ def run_ours(a):
             del arz_arena, devA, devM
             torch.cuda.empty_cache()
             line["itscp_net"] = network_bench(a, dev, dt_t, torch)
+            torch.cuda.empty_cache()
+            line["itscp_c4"] = config4_bench(a, dev, dt_t, torch)
         if not a.no_cpu_baseline:
             ra, ri, cores, sample = cpu_port_rates(a)
             line["cpu_baseline"] = {"value": ra, "unit": "cell-updates/s", "cores": cores, "kind": "port",

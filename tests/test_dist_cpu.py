@@ -73,3 +73,55 @@ def test_two_rank_shards_reduce_to_the_unsharded_result():
     assert res[0][5] + res[1][5] == [float(i) for i in range(V)]          # vehicle slices tile the batch in order
     assert [dist.shard_range(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
     assert dist.world() == (0, 1)
+
+
+def _trainer_worker(rank, ws, port, q, tmp):
+    """Two ranks train one controller on 5 episodes per epoch (3 + 2) with a stub rollout whose reward depends on the
+    episode's spawn-route draw; every rank must end with the weights of the single-process run over all 5 episodes."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    if ws > 1:
+        td.init_process_group("gloo", rank=rank, world_size=ws)
+    from dhts_b200 import dist
+    from dhts_b200.control import Trainer
+    from itscp_env_cases import c4_env, c4_fixture
+    env = c4_env(c4_fixture(), "cpu")
+    lo, _ = dist.shard_range(5, rank, ws)
+
+    def fake_rollout(action, differentiable, **kw):
+        env.flags = type("F", (), {"check": staticmethod(lambda **k: None)})()
+        R = action.shape[0]
+        tgt = 0.3 + 0.05 * (lo + torch.arange(R, dtype=torch.float64)).unsqueeze(1)      # episode-dependent target
+        return -((action.double() - tgt) ** 2).sum(1)
+    env.rollout = fake_rollout
+    torch.manual_seed(rank)                         # different initial weights per rank: the constructor must broadcast rank 0's
+    if ws == 1:
+        torch.manual_seed(0)
+    tr = Trainer(env, lr=1e-2, tensorboard=False)
+    losses = tr.train(5, 3, 1, 1, os.path.join(tmp, "ws%d" % ws))
+    flat = torch.cat([p.detach().reshape(-1) for p in tr.controller.parameters()])
+    q.put((rank, losses, flat[:64].tolist(), float(flat.double().sum())))
+    if ws > 1:
+        td.destroy_process_group()
+
+
+def test_two_rank_trainer_matches_single_process(tmp_path):
+    ctx = mp.get_context("spawn")
+    out = {}
+    for ws in (1, 2):
+        port = 31500 + os.getpid() % 2000 + ws
+        q = ctx.Queue()
+        procs = [ctx.Process(target=_trainer_worker, args=(r, ws, port, q, str(tmp_path))) for r in range(ws)]
+        for p in procs:
+            p.start()
+        out[ws] = sorted(q.get(timeout=240) for _ in range(ws))
+        for p in procs:
+            p.join(60)
+            assert p.exitcode == 0
+    single = out[1][0]
+    for rank, losses, head, total in out[2]:
+        assert max(abs(a - b) for a, b in zip(losses, single[1])) < 1e-5 * max(1.0, abs(single[1][0]))      # fp32 controller, different summation order
+        assert max(abs(a - b) for a, b in zip(head, single[2])) < 1e-5
+        assert abs(total - single[3]) < 1e-4 * max(1.0, abs(single[3]))
+    assert os.path.exists(os.path.join(str(tmp_path), "ws2", "eval.txt"))           # rank 0 alone writes the logs
