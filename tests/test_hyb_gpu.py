@@ -161,3 +161,29 @@ def test_plain_mode_chain_matches_live_reference(dev):
     assert relerr(gr[:N], g["g_r0_lane0"]) < 1e-8 and relerr(gu[:N], g["g_u0_lane0"]) < 1e-8
     assert relerr(gr[N:], g["g_r0_lane2"]) < 1e-8 and relerr(gu[N:], g["g_u0_lane2"]) < 1e-8
     assert np.abs(g["g_r0_lane0"]).max() > 0
+
+
+def test_f32_build_tracks_f64_on_a_short_horizon(dev):
+    """fp32 symbols of the hybrid rollout (tolerance stated separately from fp64): over 40 frames of fixture `h`
+    the discrete events agree and the cell states stay within 2e-4 of the fp64 run (largest entry); gradients finite."""
+    from dhts_b200 import Flags
+    from dhts_b200.hybrid_network import hybrid_rollout
+    G = fixture_case("h")
+    grid, topo = build(G, dev)
+    T, umax, dt = 40, float(G["umax"]), float(G["dt"])
+    route = torch.tensor(G["route"][:T], dtype=torch.int32, device=dev)
+    sp = torch.tensor(spawn_routes(G, topo), dtype=torch.int32, device=dev)
+    out = {}
+    for dt_t in (torch.float64, torch.float32):
+        c = lambda a: torch.tensor(np.asarray(a), dtype=dt_t, device=dev)
+        r0 = c(G["r0"][None]).requires_grad_(); u0 = c(G["u0"][None])
+        flags = Flags(dev)
+        st = hybrid_rollout(topo, r0, u0, umax, dt, T, sig=c(G["sig"][None, :T]), incoming=c(G["incoming"][None, :T]), route=route,
+                            spawn_route=sp, flags=flags)
+        (st.cells[T, :, 0].sum() + st.speed[T].sum()).backward()
+        flags.check(quiet_collisions=True)
+        out[dt_t] = (st.cells.detach().double().cpu().numpy(), st.count.cpu().numpy(), r0.grad.double().cpu().numpy())
+    a, b = out[torch.float64], out[torch.float32]
+    assert (a[1] == b[1]).all()
+    assert np.abs(a[0] - b[0]).max() < 2e-4 * np.abs(a[0]).max()
+    assert np.isfinite(b[2]).all() and relerr(b[2], a[2]) < 5e-2

@@ -98,3 +98,33 @@ def test_trainer_epoch_on_the_fused_path(dev, tmp_path):
     assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in tr.controller.parameters())
     assert any(float((p - q).abs().max()) > 0 for p, q in zip(tr.controller.parameters(), before))
     assert len(open(str(tmp_path / "trial_0" / "eval.txt")).read().splitlines()) == 2
+
+
+@pytest.mark.parametrize("n,num_lane,lane_length,mode", [(4, 1, 20.0, "hybrid"), (2, 2, 10.0, "macro"), (3, 2, 5.0, "hybrid")])
+def test_other_grids_run_clean(dev, n, num_lane, lane_length, mode):
+    """Grids the fixtures do not cover (4x4 with a 2x2 micro core where vehicles hand over micro -> micro; two lanes per
+    road; macro mode): no CFL / route / overflow flags, finite non-zero action gradients, hard evaluation finite."""
+    from dhts_b200.itscp_env import ItscpEnv, problem_2
+    np.random.seed(9)
+    env = ItscpEnv(device=dev)
+    env.schedule_callback = problem_2
+    env.config.update(num_intersection=n, num_lane=num_lane, lane_length=lane_length, policy_length=6, signal_length=2,
+                      mode=mode, speed_limit=60.0, max_spawn=32)
+    env.reset()
+    assert env.action_size() == 3 * n * n and env.hybrid == (mode == "hybrid" and n >= 3)
+    g = torch.Generator().manual_seed(1)
+    R = 3
+    act = (0.3 + 0.4 * torch.rand((R, env.action_size()), generator=g)).to(dev).double().requires_grad_()
+    env.resample_spawn_routes(R, g)
+    r = env.rollout(act, True, keep_states=True)
+    r.sum().backward()
+    bits, ncol = env.flags.check(quiet_collisions=True)
+    assert (bits & ~4) == 0
+    assert bool(torch.isfinite(r).all()) and float(r.max()) < 0
+    assert bool(torch.isfinite(act.grad).all()) and float(act.grad.abs().max()) > 0
+    if env.hybrid:
+        st = env.last["states"]
+        assert int(st.count.max()) >= 1, "vehicles must have been spawned"
+    with torch.no_grad():
+        rh = env.rollout(act.detach(), False)
+    assert bool(torch.isfinite(rh).all())
