@@ -439,6 +439,7 @@ __global__ void __launch_bounds__(HYB_THREADS_MAX) hyb_rollout_fwd_kernel(HybArg
             if (headh) {
                 T* hh = headh + ((size_t)t * a.n.R + b) * 2 * a.ML;
                 for (int c = threadIdx.x; c < 2 * a.ML; c += blockDim.x) hh[c] = s.headd[c];
+                __syncthreads();      // the next step's phase 1 rewrites s.headd (no barrier before it when phase 0 is skipped)
             }
             p ^= 1;
         }
