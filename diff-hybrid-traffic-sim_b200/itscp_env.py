@@ -111,21 +111,23 @@ def running_mean_constants(samples: torch.Tensor, valid: Optional[torch.Tensor],
                            window: int = 100_000) -> torch.Tensor:
     """``scale / |RunningMean.mean()|`` after appending each VALID sample in order (common/rms.py:3-22 as used by
     _env.py:557-575,697-702): the mean covers the last `window` valid samples up to and including the current one.
-    samples / valid are flat [M]; entries at invalid positions are meaningless.  Accumulates in float64 (the reference
-    in float32)."""
-    d = samples.detach().reshape(-1).to(torch.float64)
-    if valid is None:
-        valid = torch.ones_like(d, dtype=torch.bool)
-    m = valid.reshape(-1)
+    samples / valid are [M] or [R, M] (R independent sequences, one RunningMean each); entries at invalid positions are
+    meaningless.  Accumulates in float64 (the reference in float32)."""
+    shape = samples.shape
+    d = samples.detach().to(torch.float64).reshape(-1, shape[-1]) if samples.dim() > 1 else samples.detach().to(torch.float64).reshape(1, -1)
+    m = torch.ones_like(d, dtype=torch.bool) if valid is None else valid.reshape(d.shape)
     d = torch.where(m, d, torch.zeros_like(d))
-    cs = torch.cumsum(d, 0)
-    n = torch.cumsum(m.to(torch.int64), 0)
+    cs = torch.cumsum(d, 1)
+    n = torch.cumsum(m.to(torch.int64), 1)
     cnt = torch.clamp(n, max=window)
     over = n - window                                    # how many valid samples have left the window
-    first = torch.searchsorted(n, torch.clamp(over, min=1))      # position of the `over`-th valid sample
-    drop = torch.where(over > 0, cs[torch.clamp(first, max=d.numel() - 1)], torch.zeros_like(cs))
+    if int(n[:, -1].max()) > window:
+        first = torch.searchsorted(n, torch.clamp(over, min=1))      # position of the `over`-th valid sample, row by row
+        drop = torch.where(over > 0, torch.gather(cs, 1, torch.clamp(first, max=d.shape[1] - 1)), torch.zeros_like(cs))
+    else:
+        drop = torch.zeros_like(cs)
     mean = (cs - drop) / torch.clamp(cnt, min=1).to(torch.float64)
-    return scale / mean.abs()
+    return (scale / mean.abs()).reshape(shape)
 
 
 class ItscpEnv:
@@ -351,7 +353,7 @@ class ItscpEnv:
         d = static - speed                                                                    # [R, T, S]
         if differentiable:       # _env.py:557-575: sigmoid with the running-mean constant, samples in lane-id order
             do, mo = d[..., self._order], mask[..., self._order]
-            k = torch.stack([running_mean_constants(do[b], mo[b]).reshape(T, -1) for b in range(R)])
+            k = running_mean_constants(do.reshape(R, -1), mo.reshape(R, -1)).reshape(R, T, -1)      # one RunningMean per episode
             k = k[..., self._inv_order].to(dtype)
             is_static = torch.sigmoid(torch.clamp(d * k, -16.0, 16.0))
         else:                    # _env.py:576-586
