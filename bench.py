@@ -552,7 +552,7 @@ def run_ours(a):
             line["itscp_net"] = network_bench(a, dev, dt_t, torch)
             torch.cuda.empty_cache()
             line["itscp_c4"] = config4_bench(a, dev, dt_t, torch)
-        if not a.no_cpu_baseline:
+        if not a.no_cpu_baseline and world == 1:      # the CPU leg is reported at N = 1 only
             ra, ri, cores, sample = cpu_port_rates(a)
             line["cpu_baseline"] = {"value": ra, "unit": "cell-updates/s", "cores": cores, "kind": "port",
                                     "sample": sample, "idm_value": ri, "idm_unit": "vehicle-updates/s"}

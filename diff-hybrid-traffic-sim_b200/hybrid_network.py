@@ -274,6 +274,7 @@ class HybRolloutFn(torch.autograd.Function):
     def forward(ctx, r0, y0, u0, own0, sig, incoming, aux0, topo: HybridNetTopology, route, spawn_route, veh_par, umax, dt,
                 steps, soft, flags):
         dev = _lib.require_cuda(r0, y0, u0, own0, sig, incoming, aux0, route, spawn_route, flags)
+        ctx.set_materialize_grads(False)      # an output nobody differentiates stays None in backward (no zero-filled history)
         c = lambda t: None if t is None else t.contiguous()
         r0, y0, u0, own0, sig, incoming, aux0, route, spawn_route = map(c, (r0, y0, u0, own0, sig, incoming, aux0, route, spawn_route))
         R, NC = r0.shape

@@ -133,6 +133,7 @@ class NetRolloutFn(torch.autograd.Function):
     def forward(ctx, r0, y0, u0, own0, sig, incoming, topo: MacroNetTopology, route, qk, umax, dt, veh_len,
                 static_speed, steps, soft, flags):
         dev = _lib.require_cuda(r0, y0, u0, own0, sig, incoming, route, qk, flags)
+        ctx.set_materialize_grads(False)      # an output nobody differentiates stays None in backward (no zero-filled history)
         c = lambda t: None if t is None else t.contiguous()
         r0, y0, u0, own0, sig, incoming, route, qk = map(c, (r0, y0, u0, own0, sig, incoming, route, qk))
         R, NC = r0.shape
