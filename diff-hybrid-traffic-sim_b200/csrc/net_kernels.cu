@@ -30,6 +30,7 @@
 // ghosts, runs the flux-difference adjoint over its cells, pulls the ghost adjoint back through from_r_u and the
 // blend, and publishes (d green, d signal) per side in shared memory; after one barrier each lane GATHERS what its
 // neighbours published for its edge cells and for its signal (fixed order: deterministic, no atomics).
+#include <cuda_pipeline.h>
 #include "dhts_net.cuh"
 
 namespace dhts {
@@ -133,11 +134,15 @@ __global__ void __launch_bounds__(256) net_rollout_bwd_kernel(NetArgs<T> a, cons
     extern __shared__ __align__(16) unsigned char raw[];
     T* sm = reinterpret_cast<T*>(raw);
     const int NC = a.NC, L = a.L;
+    // three rotating state buffers: state t (cur), state t + 1 (nxt) and the row being prefetched for the next step
+    // (pre); the stored rows stream in with cp.async (LDGSTS) one step ahead of the arithmetic
     T* cur = sm;                        // state t      (r, y, u)
     T* nxt = sm + 3 * NC;               // state t + 1  (r, y, u)
-    T* G = sm + 6 * NC;                 // adjoint of state t+1 on entry of a step, of state t on exit: (gr, gy, gu)
-    T* own = sm + 9 * NC;               // own records at step t
-    T* GO = own + 2 * a.n_own;          // adjoint of the own records
+    T* pre = sm + 6 * NC;               // state t - 1, in flight
+    T* G = sm + 9 * NC;                 // adjoint of state t+1 on entry of a step, of state t on exit: (gr, gy, gu)
+    T* own = sm + 12 * NC;              // own records at step t
+    T* own_pre = own + 2 * a.n_own;     // own records at step t - 1, in flight
+    T* GO = own_pre + 2 * a.n_own;      // adjoint of the own records
     T* pub = GO + 2 * a.n_own;          // [L][2 sides][3] published (d green r, d green u, d signal)
     const T inv_umax = T(1) / a.umax, inv15 = T(1) / (T(1.5) * a.umax);
     for (int b = blockIdx.x; b < a.R; b += gridDim.x) {
@@ -152,15 +157,19 @@ __global__ void __launch_bounds__(256) net_rollout_bwd_kernel(NetArgs<T> a, cons
         }
         const T grew = g_reward ? g_reward[b] : T(0);
         bool nan = false;
+#define DHTS_NET_PREFETCH(TT, DST, ODST)                                                                               \
+        {                                                                                                              \
+            const T* h_ = hist + ((size_t)(TT) * a.R + b) * 3 * NC;                                                    \
+            for (int c = threadIdx.x; c < 3 * NC; c += blockDim.x) __pipeline_memcpy_async((DST) + c, h_ + c, sizeof(T)); \
+            const T* oh_ = ownh + ((size_t)(TT) * a.R + b) * 2 * a.n_own;                                              \
+            for (int c = threadIdx.x; c < 2 * a.n_own; c += blockDim.x) __pipeline_memcpy_async((ODST) + c, oh_ + c, sizeof(T)); \
+            __pipeline_commit();                                                                                       \
+        }
+        if (a.T_steps > 0) DHTS_NET_PREFETCH(a.T_steps - 1, cur, own)
         for (int t = a.T_steps - 1; t >= 0; t--) {
-            __syncthreads();
-            {
-                const T* h = hist + ((size_t)t * a.R + b) * 3 * NC;
-                for (int c = threadIdx.x; c < 3 * NC; c += blockDim.x) cur[c] = h[c];
-                const T* oh = ownh + ((size_t)t * a.R + b) * 2 * a.n_own;
-                for (int c = threadIdx.x; c < 2 * a.n_own; c += blockDim.x) own[c] = oh[c];
-            }
-            __syncthreads();
+            __pipeline_wait_prior(0);
+            __syncthreads();          // state t has landed; the previous step's gathers are complete
+            if (t > 0) DHTS_NET_PREFETCH(t - 1, pre, own_pre)          // pre was state t + 2: nobody reads it any more
             const T* cr = cur; const T* cy = cur + NC; const T* cu = cur + 2 * NC;
             const int* rt = a.route ? a.route + (size_t)b * a.route_stride + (size_t)t * 2 * L : nullptr;
             const T* sig_t = a.sig ? a.sig + ((size_t)b * a.T_steps + t) * L : nullptr;
@@ -279,9 +288,9 @@ __global__ void __launch_bounds__(256) net_rollout_bwd_kernel(NetArgs<T> a, cons
                     }
                 }
             }
-            __syncthreads();
-            for (int c = threadIdx.x; c < 3 * NC; c += blockDim.x) nxt[c] = cur[c];
+            { T* x_ = nxt; nxt = cur; cur = pre; pre = x_; x_ = own; own = own_pre; own_pre = x_; }     // rotate: no copy, no barrier
         }
+#undef DHTS_NET_PREFETCH
         __syncthreads();
         for (int c = threadIdx.x; c < NC; c += blockDim.x) {
             g_r0[(size_t)b * NC + c] = G[c]; g_y0[(size_t)b * NC + c] = G[NC + c]; g_u0[(size_t)b * NC + c] = G[2 * NC + c];
@@ -306,7 +315,7 @@ static int net_sm_count() {
 static int net_threads(int L) { int t = (L + 31) / 32 * 32; return t > 256 ? 256 : (t < 32 ? 32 : t); }
 
 template <typename T> static size_t net_smem(int L, int NC, int n_own, bool adj, int threads) {
-    return sizeof(T) * (adj ? ((size_t)9 * NC + 4 * n_own + (size_t)6 * L) : ((size_t)6 * NC + 4 * n_own + threads)) + 16;
+    return sizeof(T) * (adj ? ((size_t)12 * NC + 6 * n_own + (size_t)6 * L) : ((size_t)6 * NC + 4 * n_own + threads)) + 16;
 }
 
 template <typename T>
