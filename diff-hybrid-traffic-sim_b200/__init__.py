@@ -13,7 +13,7 @@ from ._lib import Flags, UnsupportedShape  # noqa: F401
 def __getattr__(name):
     # torch-facing modules are imported lazily so that `build()` works before the .so exists
     if name in ("ops", "functional", "dist", "dropin", "network", "itscp", "hybrid_network", "itscp_env", "control",
-                "inverse", "run_itscp"):
+                "inverse", "run_itscp", "run_inverse"):
         import importlib
         return importlib.import_module(__name__ + "." + name)
     raise AttributeError(name)

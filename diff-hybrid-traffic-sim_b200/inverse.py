@@ -153,6 +153,57 @@ class InverseBatch:
             pick = lambda s: tuple(x[rows] for x in s)
             return self.compute_error(pick(self.beg_state), st), self.compute_error(pick(self.end_state), end)
 
+    def solve_scipy(self, est_row: State, method: str, trial: int):
+        """_inverse.py:301-352 for ONE trial: Nelder-Mead / SLSQP from scipy over ``evaluate_vector_states``; every objective
+        call is logged, the lists are padded / cut to ``num_episode`` as the reference does.  SLSQP's finite-difference
+        gradient (2n probes) is evaluated as ONE batched launch instead of 2n sequential simulations."""
+        import numpy as np
+        import scipy.optimize
+        lb, ub = self.bounds()
+        bounds = scipy.optimize.Bounds(th.cat([lb[0], lb[1]]).cpu().numpy(), th.cat([ub[0], ub[1]]).cpu().numpy())
+        x0 = self.vectorize(tuple(self._dev(s) for s in est_row)).cpu().numpy()
+        beg_errors: List[float] = []
+        end_errors: List[float] = []
+
+        def fun(v):
+            b, e = self.evaluate_vector_states(th.as_tensor(np.asarray(v)[None]), trial)
+            beg_errors.append(float(b[0])); end_errors.append(float(e[0]))
+            return float(e[0])
+
+        def jac(v):      # forward differences with scipy's default relative step, all probes in one batch
+            v = np.asarray(v, dtype=np.float64)
+            h = np.sqrt(np.finfo(np.float64).eps) * np.maximum(1.0, np.abs(v))
+            probes = np.concatenate([v[None], v[None] + np.diag(h)])
+            _, e = self.evaluate_vector_states(th.as_tensor(probes), trial)
+            e = e.cpu().numpy()
+            return (e[1:] - e[0]) / h
+
+        kw = dict(fun=fun, x0=x0, bounds=bounds, options={"maxiter": self.num_episode + 1}, method=method)
+        if method == "SLSQP":
+            kw["jac"] = jac
+        scipy.optimize.minimize(**kw)
+        while len(beg_errors) < self.num_episode:
+            beg_errors.append(beg_errors[-1]); end_errors.append(end_errors[-1])
+        return beg_errors[:self.num_episode], end_errors[:self.num_episode]
+
+    def solve_cma(self, est_row: State, sigma: float, trial: int):
+        """_inverse.py:245-299 for ONE trial: ask / tell CMA-ES (the optional ``cma`` package) with every population
+        evaluated as one batch."""
+        from math import ceil
+        import cma      # not a dependency of this repository: pip install cma
+        lb, ub = self.bounds()
+        opts = cma.CMAOptions(); opts.set("bounds", [th.cat([lb[0], lb[1]]).cpu().tolist(), th.cat([ub[0], ub[1]]).cpu().tolist()])
+        opts.set("verbose", -1)
+        es = cma.CMAEvolutionStrategy(self.vectorize(tuple(self._dev(s) for s in est_row)).cpu().numpy(), sigma, opts)
+        beg_errors: List[float] = []
+        end_errors: List[float] = []
+        for _ in range(ceil(self.num_episode / es.popsize)):
+            sol = es.ask()
+            b, e = self.evaluate_vector_states(th.as_tensor(sol), trial)
+            beg_errors.extend(b.cpu().tolist()); end_errors.extend(e.cpu().tolist())
+            es.tell(sol, e.cpu().tolist())
+        return beg_errors[:self.num_episode], end_errors[:self.num_episode]
+
     def write_trials(self, method: str, beg_errors, end_errors) -> List[str]:
         """``<log_dir>/<method dir>/trial_<k>.txt`` for every trial (_inverse.py:162-166)."""
         d = os.path.join(self.log_dir, self.method_dir.get(method, method))

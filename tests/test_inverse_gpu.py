@@ -83,3 +83,34 @@ def test_seeded_initialize_and_trials_are_independent(dev, tmp_path):
         assert 0 < float(d) < 0.06                                             # estimate = truth + N(0, 1e-2), clamped
     assert np.array_equal(curves[0][:, :2], curves[1])
     assert (curves[0][-1] < curves[0][0]).all()                               # Adam reduces every trial's error
+
+
+def test_scipy_solvers_over_the_batched_objective(dev, tmp_path):
+    """Nelder-Mead and SLSQP (_inverse.py:301-352) over evaluate_vector_states: error lists of num_episode entries, the
+    first entry is the error of the initial estimate, SLSQP (batched finite-difference gradient) reduces the error."""
+    from dhts_b200.inverse import MacroInverseBatch
+    torch.manual_seed(5)
+    prob = MacroInverseBatch(2, 100, 12, 0.01, 30.0, "s", 10, 5.0, device=dev, log_root=str(tmp_path))
+    est = prob.initialize()
+    row = tuple(s[1] for s in est)
+    b0, e0 = prob.evaluate_vector_states(prob.vectorize(row)[None], 1)
+    for method in ("Nelder-Mead", "SLSQP"):
+        beg, end = prob.solve_scipy(row, method, 1)
+        assert len(beg) == len(end) == 12 and abs(end[0] - float(e0[0])) < 1e-12 and abs(beg[0] - float(b0[0])) < 1e-12
+        assert min(end) <= end[0]
+        if method == "SLSQP":
+            assert min(end) < 0.9 * end[0]
+
+
+def test_run_inverse_cli_writes_the_reference_tree(dev, tmp_path):
+    import os
+    from dhts_b200.run_inverse import main
+    for problem in ("macro", "micro", "hybrid"):
+        out = main(["--problem", problem, "--n_trial", "3", "--n_timestep", "120", "--n_episode", "5", "--seed", "3",
+                    "--log_root", str(tmp_path)])
+        d = os.path.join(out["run"], "gd")
+        assert sorted(os.listdir(d)) == ["trial_0.txt", "trial_1.txt", "trial_2.txt"]
+        rows = [l.split() for l in open(os.path.join(d, "trial_1.txt"))]
+        assert len(rows) == 5 and all(len(r) == 2 for r in rows)
+        last, first = out["methods"]["gd"]["end_error_last"], out["methods"]["gd"]["end_error_first"]
+        assert all(np.isfinite(last)) and sum(last) < sum(first)
