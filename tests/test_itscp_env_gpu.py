@@ -128,3 +128,18 @@ def test_other_grids_run_clean(dev, n, num_lane, lane_length, mode):
     with torch.no_grad():
         rh = env.rollout(act.detach(), False)
     assert bool(torch.isfinite(rh).all())
+
+
+def test_run_itscp_cli_writes_the_reference_tree(dev, tmp_path):
+    """python -m dhts_b200.run_itscp with run.py's arguments: <out>/trial_<k>/{eval.txt, model.zip, best/model.zip}."""
+    import os
+    from dhts_b200.run_itscp import main
+    out = str(tmp_path / "hybrid_0")
+    curves = main(["--mode=hybrid", "--problem=2", "--n_trial=2", "--n_intersection=3", "--n_lane=1", "--lane_length=5",
+                   "--speed_limit=60", "--simulation_length=4", "--signal_length=2", "--n_episode=3", "--lr=1e-4",
+                   "--episodes_per_epoch=2", "--seed=3", "--out", out])
+    assert len(curves) == 2 and all(len(c) == 4 and np.isfinite(c).all() for c in curves)       # n_episode + 1 epochs (run.py:70)
+    for k in range(2):
+        d = os.path.join(out, "trial_%d" % k)
+        assert os.path.exists(d + "/model.zip") and os.path.exists(d + "/best/model.zip")
+        assert len(open(d + "/eval.txt").read().split()) == 4                                   # evaluation every max(3 // 10, 1) = 1 epoch
