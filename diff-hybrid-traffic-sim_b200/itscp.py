@@ -144,20 +144,22 @@ class ItscpGrid:
 
 
 # ---------------------------------------------------------------------- queue-length reward, exact constants
-def queue_constants(u_states: torch.Tensor, static_speed: float, window: int = 100_000, start_sum: float = 0.0,
-                    start_count: int = 0) -> torch.Tensor:
+def queue_constants(u_states: torch.Tensor, static_speed: float, window: int = 100_000) -> torch.Tensor:
     """Sigmoid constant 16 / |running mean| the reference applies to every cell sample (_env.py:557-575):
     before each sigmoid the sample (static_speed - u) is appended to a RunningMean over the last `window` samples
-    (common/rms.py), visiting frames, lanes and cells in order.  u_states [T, NC] (one replica, states AFTER each
-    step, cells lane by lane) -> constants [T, NC].  The reference accumulates in float32; this is float64."""
-    d = (static_speed - u_states.detach()).reshape(-1).to(torch.float64)
-    cs = torch.cumsum(d, 0)
-    n = torch.arange(1, d.numel() + 1, device=d.device)
+    (common/rms.py), visiting frames, lanes and cells in order.  u_states [T, NC] (one replica) or [R, T, NC] (one
+    RunningMean per replica), states AFTER each step, cells lane by lane -> constants of the same shape.  The reference
+    accumulates in float32; this is float64."""
+    shape = u_states.shape
+    d = (static_speed - u_states.detach()).to(torch.float64)
+    d = d.reshape(1, -1) if d.dim() == 2 else d.reshape(shape[0], -1)
+    cs = torch.cumsum(d, 1)
+    n = torch.arange(1, d.shape[1] + 1, device=d.device)
     lo = n - window
-    drop = torch.where(lo > 0, cs[torch.clamp(lo - 1, min=0)], torch.zeros_like(cs))
+    drop = torch.where(lo > 0, cs[:, torch.clamp(lo - 1, min=0)], torch.zeros_like(cs))
     cnt = torch.clamp(n, max=window).to(torch.float64)
     mean = (cs - drop) / cnt
-    return (16.0 / mean.abs()).reshape(u_states.shape).to(u_states.dtype)
+    return (16.0 / mean.abs()).reshape(shape).to(u_states.dtype)
 
 
 def queue_reward(states: torch.Tensor, topo: MacroNetTopology, dt: float, veh_len: float, static_speed: float,
@@ -206,7 +208,7 @@ class ItscpBatch:
         if exact_constants:
             u_after = states[1:, :, 2].transpose(0, 1)
             if differentiable:
-                k = torch.stack([queue_constants(u_after[b], self.static_speed) for b in range(R)])
+                k = queue_constants(u_after, self.static_speed)
             else:   # hard test: speed < static_speed (_env.py:576-586)
                 k = torch.full_like(u_after, 1e30)
             reward = queue_reward(states, self.topo, self.dt, self.veh_len, self.static_speed, k)
