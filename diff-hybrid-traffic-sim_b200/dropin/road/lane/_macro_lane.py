@@ -57,6 +57,7 @@ class MacroLane(BaseLane):
         self.bdry_callback_args = {"lane": self}
         self._views = {"curr": None, "next": None}      # field -> rt.Views of the device vectors
         self._ghost_src = {}                            # side -> (r, u) objects the ghost was derived from
+        self._ghost_dev = {}                            # (cell id, field) -> (source object, [1] device tensor, (dtype, device))
 
     def is_macro(self):
         return True
@@ -84,7 +85,18 @@ class MacroLane(BaseLane):
         return rt.gather([_get(c, k) for c in cells])
 
     def _ghost(self, cell, k):
-        return rt.scalar(_get(cell, k)).reshape(1)
+        """[1] device tensor of a ghost-cell field; cached while the cell keeps the very same constant object (static ghosts
+        are set once, road_network.py:312-321), so a step does not pay eight host->device copies for them."""
+        v = _get(cell, k)
+        if rt.is_tensor(v) and v.requires_grad:
+            return rt.scalar(v).reshape(1)
+        key = (id(cell), k)
+        hit = self._ghost_dev.get(key)
+        if hit is not None and hit[0] is v and hit[2] == (rt.store_dtype(), rt.device()):
+            return hit[1]
+        t = rt.scalar(v).reshape(1)
+        self._ghost_dev[key] = (v, t, (rt.store_dtype(), rt.device()))
+        return t
 
     def _padded(self, k, detach=False):
         """[N+2] = (left ghost, cells, right ghost), the operator's input layout (dmacro_lane.py:134-158)."""

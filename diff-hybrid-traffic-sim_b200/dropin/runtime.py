@@ -29,9 +29,11 @@ def configure(precision=None, device=None):
 
 def device() -> torch.device:
     """The CUDA device the lanes live on.  Fails loudly without one: the step has no CPU path."""
-    if not torch.cuda.is_available():
-        raise RuntimeError("dhts drop-in lanes need a CUDA device: the simulation step runs only in the sm_100a "
-                           "kernels of libdhts_b200.so (no CPU fallback)")
+    if not _cfg.get("cuda_ok"):                 # asked once per process: the call is on the per-step path
+        if not torch.cuda.is_available():
+            raise RuntimeError("dhts drop-in lanes need a CUDA device: the simulation step runs only in the sm_100a "
+                               "kernels of libdhts_b200.so (no CPU fallback)")
+        _cfg["cuda_ok"] = True
     d = _cfg["device"]
     return torch.device(d) if d else torch.device("cuda", torch.cuda.current_device())
 
