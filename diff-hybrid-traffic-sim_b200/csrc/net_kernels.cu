@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256) net_rollout_fwd_kernel(NetArgs<T> a, cons
 // g_reward [R]            optional: dLoss/d reward (fused queue reward)
 // outputs: g_r0, g_y0, g_u0 [R][NC]; g_own0 [R][n_own][2]; g_sig, g_inc [R][T][L]
 template <typename T>
-__global__ void __launch_bounds__(256) net_rollout_bwd_kernel(NetArgs<T> a, const T* __restrict__ hist, const T* __restrict__ ownh,
+__global__ void __launch_bounds__(256, 2) net_rollout_bwd_kernel(NetArgs<T> a, const T* __restrict__ hist, const T* __restrict__ ownh,
                                                                const T* __restrict__ g_states, const T* __restrict__ g_reward,
                                                                T* __restrict__ g_r0, T* __restrict__ g_y0, T* __restrict__ g_u0,
                                                                T* __restrict__ g_own0, T* __restrict__ g_sig,
