@@ -35,6 +35,22 @@
 
 namespace dhts {
 
+// Thread -> lane assignment: lanes sorted by their number of cells (stable), so that the threads of a warp sweep lanes
+// of equal length (an ITSCP grid mixes 1-, 2- and 4-cell lanes: in lane-id order a warp ran at 56 % thread efficiency,
+// profiles/r1n_net_ncu_summary.json).  order[rank] = lane; every thread calls it; ends with a block barrier.
+template <typename T> __device__ __forceinline__ void lane_order(const NetArgs<T>& a, int* order) {
+    for (int l = threadIdx.x; l < a.L; l += blockDim.x) {
+        const int n = a.cell_off[l + 1] - a.cell_off[l];
+        int rank = 0;
+        for (int j = 0; j < a.L; j++) {
+            const int m = a.cell_off[j + 1] - a.cell_off[j];
+            rank += (m > n) || (m == n && j < l);
+        }
+        order[rank] = l;
+    }
+    __syncthreads();
+}
+
 // ------------------------------------------------------------------------------------------------ forward
 // hist  [T+1][R][3][NC]  state (r, y, u) before step t (t = 0..T-1) and after the last step
 // ownh  [T+1][R][n_own][2] carried own-ghost records, same indexing
@@ -49,7 +65,9 @@ __global__ void __launch_bounds__(256) net_rollout_fwd_kernel(NetArgs<T> a, cons
     T* buf[2] = {sm, sm + 3 * NC};                         // (r, y, u) x NC, double buffered
     T* own[2] = {sm + 6 * NC, sm + 6 * NC + 2 * a.n_own};
     T* red = sm + 6 * NC + 4 * a.n_own;                    // [blockDim] reward reduction
+    int* order = reinterpret_cast<int*>(red + blockDim.x);  // [L] lanes by decreasing number of cells
     const T inv_umax = T(1) / a.umax, inv15 = T(1) / (T(1.5) * a.umax);
+    lane_order(a, order);
     for (int b = blockIdx.x; b < a.R; b += gridDim.x) {
         __syncthreads();
         for (int c = threadIdx.x; c < NC; c += blockDim.x) {
@@ -73,7 +91,8 @@ __global__ void __launch_bounds__(256) net_rollout_fwd_kernel(NetArgs<T> a, cons
             const int* rt = a.route ? a.route + (size_t)b * a.route_stride + (size_t)t * 2 * L : nullptr;
             const T* sig_t = a.sig ? a.sig + ((size_t)b * a.T_steps + t) * L : nullptr;
             const T* inc_t = a.incoming ? a.incoming + ((size_t)b * a.T_steps + t) * L : nullptr;
-            for (int l = threadIdx.x; l < L; l += blockDim.x) {
+            for (int li = threadIdx.x; li < L; li += blockDim.x) {
+                const int l = order[li];
                 const int c0 = a.cell_off[l], N = a.cell_off[l + 1] - c0;
                 const T dxl = a.dx[l], cc = a.dt / dxl;
                 const Side<T> sl = resolve_side(a, l, 0, rt, cr, cu, own[p], sig_t, inc_t, bad_route);
@@ -144,7 +163,9 @@ __global__ void __launch_bounds__(256, 2) net_rollout_bwd_kernel(NetArgs<T> a, c
     T* own_pre = own + 2 * a.n_own;     // own records at step t - 1, in flight
     T* GO = own_pre + 2 * a.n_own;      // adjoint of the own records
     T* pub = GO + 2 * a.n_own;          // [L][2 sides][3] published (d green r, d green u, d signal)
+    int* order = reinterpret_cast<int*>(pub + (size_t)6 * L);      // [L] lanes by decreasing number of cells
     const T inv_umax = T(1) / a.umax, inv15 = T(1) / (T(1.5) * a.umax);
+    lane_order(a, order);
     for (int b = blockIdx.x; b < a.R; b += gridDim.x) {
         __syncthreads();
         {   // terminal state and adjoint
@@ -175,7 +196,8 @@ __global__ void __launch_bounds__(256, 2) net_rollout_bwd_kernel(NetArgs<T> a, c
             const T* sig_t = a.sig ? a.sig + ((size_t)b * a.T_steps + t) * L : nullptr;
             const T* inc_t = a.incoming ? a.incoming + ((size_t)b * a.T_steps + t) * L : nullptr;
             bool dummy = false;
-            for (int l = threadIdx.x; l < L; l += blockDim.x) {
+            for (int li = threadIdx.x; li < L; li += blockDim.x) {
+                const int l = order[li];
                 const int c0 = a.cell_off[l], N = a.cell_off[l + 1] - c0;
                 const T dxl = a.dx[l], cc = a.dt / dxl;
                 // (1) fused queue reward of state t+1 and the stored speed's adjoint folded into (r, y)
@@ -256,7 +278,8 @@ __global__ void __launch_bounds__(256, 2) net_rollout_bwd_kernel(NetArgs<T> a, c
             }
             __syncthreads();
             // (4) gathers: what the neighbours took from this lane's edge cells and from its signal
-            for (int l = threadIdx.x; l < L; l += blockDim.x) {
+            for (int li = threadIdx.x; li < L; li += blockDim.x) {
+                const int l = order[li];
                 const int c0 = a.cell_off[l], N = a.cell_off[l + 1] - c0;
                 T gsig = pub[((size_t)l * 2 + 1) * 3 + 2];
                 // successors whose LEFT ghost came from this lane's last cell / was blended by this lane's signal
@@ -315,7 +338,7 @@ static int net_sm_count() {
 static int net_threads(int L) { int t = (L + 31) / 32 * 32; return t > 256 ? 256 : (t < 32 ? 32 : t); }
 
 template <typename T> static size_t net_smem(int L, int NC, int n_own, bool adj, int threads) {
-    return sizeof(T) * (adj ? ((size_t)12 * NC + 6 * n_own + (size_t)6 * L) : ((size_t)6 * NC + 4 * n_own + threads)) + 16;
+    return sizeof(T) * (adj ? ((size_t)12 * NC + 6 * n_own + (size_t)6 * L) : ((size_t)6 * NC + 4 * n_own + threads)) + sizeof(int) * (size_t)L + 16;
 }
 
 template <typename T>
