@@ -181,7 +181,24 @@ template <typename T> struct HybSm {
     T* headd;     // [ML][2] head deltas the IDM step used
     T* mid;       // adjoint kernel: (r, y, u) x NC between update and conversions
     ConvLog<T> log;
+    int* order;   // [L] thread -> lane assignment: macro lanes by decreasing number of cells, then the micro lanes
 };
+
+// Lanes sorted (stably) so that the threads of a warp do the same kind of work: macro lanes of equal length together,
+// micro lanes together.  Every thread calls it once per kernel; ends with a block barrier.
+template <typename T> __device__ __forceinline__ void hyb_lane_order(const HybArgs<T>& a, int* order) {
+    const NetArgs<T>& n = a.n;
+    for (int l = threadIdx.x; l < n.L; l += blockDim.x) {
+        const int key = n.kind[l] ? -1 : n.cell_off[l + 1] - n.cell_off[l];
+        int rank = 0;
+        for (int j = 0; j < n.L; j++) {
+            const int kj = n.kind[j] ? -1 : n.cell_off[j + 1] - n.cell_off[j];
+            rank += (kj > key) || (kj == key && j < l);
+        }
+        order[rank] = l;
+    }
+    __syncthreads();
+}
 
 // One simulation step of replica b: state `p` -> state `p ^ 1` of the double buffers.  All threads of the CTA call it.
 // REC: keep the state between update and conversions (s.mid) and the conversion events (s.log).
@@ -211,7 +228,8 @@ __device__ __forceinline__ void hyb_step(const HybArgs<T>& a, const HybSm<T>& s,
     }
     // ---- phase 1: every lane takes its step from the state before the step (Jacobi)
     bool bad = false, bad_route = false;
-    for (int l = threadIdx.x; l < L; l += blockDim.x) {
+    for (int li = threadIdx.x; li < L; li += blockDim.x) {
+        const int l = s.order[li];
         if (n.kind[l] == 0) {
             const int c0 = n.cell_off[l], N = n.cell_off[l + 1] - c0;
             const T dxl = n.dx[l], cc = n.dt / dxl;
@@ -396,6 +414,7 @@ template <typename T> __device__ __forceinline__ HybSm<T> hyb_carve(const HybArg
         s.mid = q; q += 3 * NC;
         s.log.et = q; q += (size_t)a.NGL * (3 + a.MAXT);
     }
+    s.order = reinterpret_cast<int*>(q); q += ((size_t)a.n.L * sizeof(int) + sizeof(T) - 1) / sizeof(T);
     extra = q;
     return s;
 }
@@ -412,6 +431,7 @@ __global__ void __launch_bounds__(HYB_THREADS_MAX) hyb_rollout_fwd_kernel(HybArg
     extern __shared__ __align__(16) unsigned char raw[];
     T* extra;
     const HybSm<T> s = hyb_carve(a, raw, false, extra);
+    hyb_lane_order(a, s.order);
     const int NC = a.n.NC, AUX = a.ax.AUX, n_own = a.n.n_own;
     unsigned fl = 0; int ncol = 0;
     for (int b = blockIdx.x; b < a.n.R; b += gridDim.x) {
@@ -464,6 +484,7 @@ __global__ void __launch_bounds__(HYB_THREADS_MAX) hyb_rollout_bwd_kernel(HybArg
     extern __shared__ __align__(16) unsigned char raw[];
     T* q;
     HybSm<T> s = hyb_carve(a, raw, true, q);
+    hyb_lane_order(a, s.order);
     const NetArgs<T>& n = a.n;
     const AuxL& x = a.ax;
     const int NC = n.NC, L = n.L, AUX = x.AUX, n_own = n.n_own, ML = a.ML, cap = a.cap;
@@ -560,7 +581,8 @@ __global__ void __launch_bounds__(HYB_THREADS_MAX) hyb_rollout_bwd_kernel(HybArg
             __syncthreads();
             // ---- R2: every lane's operator reversed
             bool dummy = false;
-            for (int l = threadIdx.x; l < L; l += blockDim.x) {
+            for (int li = threadIdx.x; li < L; li += blockDim.x) {
+                const int l = s.order[li];
                 if (n.kind[l] == 0) {
                     const int c0 = n.cell_off[l], N = n.cell_off[l + 1] - c0;
                     const T dxl = n.dx[l], cc = n.dt / dxl;
@@ -770,6 +792,7 @@ template <typename T> static size_t hyb_smem(const HybArgs<T>& a, bool adj) {
         el += 3 * NC + 2 * (size_t)a.n.n_own + 3 * ML * a.cap + a.NCAP + 6 * L + 5 * ML;
         bytes += sizeof(int) * (4 * ML + 4 * (size_t)a.NGL);
     }
+    bytes += sizeof(int) * L + sizeof(T);                                  // order
     return sizeof(T) * el + bytes + 32;
 }
 

@@ -20,7 +20,7 @@ def timed(name, fn):
 H.HybRolloutFn.forward = staticmethod(timed("kernel_fwd", orig_fwd))
 H.HybRolloutFn.backward = staticmethod(timed("kernel_bwd", orig_bwd))
 g = torch.Generator().manual_seed(3)
-for R in (1, 256):
+for R in (1, 256, 2048):
     act = (0.3 + 0.4 * torch.rand((R, 45), generator=g)).double().to(dev).requires_grad_()
     env.resample_spawn_routes(R, g)
     for it in range(4):
