@@ -39,6 +39,7 @@
 // group, the IDM / ARZ operators per lane, the ghost / head-delta blends, and gathers of everything a lane's
 // neighbours took from it (fixed order, no atomics).
 #include <cmath>
+#include <cuda_pipeline.h>
 #include "dhts_net.cuh"
 #include "dhts_idm.cuh"
 
@@ -473,8 +474,10 @@ __global__ void __launch_bounds__(HYB_THREADS_MAX) hyb_rollout_fwd_kernel(HybArg
 // dLoss/d(p, v, a) of the vehicles AFTER step t, by slot (other entries of the row are ignored).
 // outputs: g_r0, g_y0, g_u0 [R][NC]; g_own0 [R][n_own][2]; g_sig, g_inc [R][T][L]; g_aux0 [R][AUX] (p, v, a and
 // capacitor entries; the rest zero).
-template <typename T>
-__global__ void __launch_bounds__(HYB_THREADS_MAX) hyb_rollout_bwd_kernel(HybArgs<T> a, const T* __restrict__ hist, const T* __restrict__ ownh,
+// TMAX: largest CTA this instantiation is launched with.  Networks of up to 192 lanes (ITSCP 3 x 3: 144) get the
+// 170-register budget of two CTAs per SM; larger ones the full register file.
+template <typename T, int TMAX>
+__global__ void __launch_bounds__(TMAX, TMAX <= 192 ? 2 : 1) hyb_rollout_bwd_kernel(HybArgs<T> a, const T* __restrict__ hist, const T* __restrict__ ownh,
                                                                           const T* __restrict__ auxh, const T* __restrict__ g_states,
                                                                           const T* __restrict__ g_aux, T* __restrict__ g_r0,
                                                                           T* __restrict__ g_y0, T* __restrict__ g_u0,
@@ -492,6 +495,11 @@ __global__ void __launch_bounds__(HYB_THREADS_MAX) hyb_rollout_bwd_kernel(HybArg
     T* GO = q; q += 2 * n_own;                 // adjoint of the own ghost records
     T* GV = q; q += 3 * ML * cap;              // adjoint of the vehicles (gp, gv, ga) x [ML][cap]
     T* GC = q; q += a.NCAP;                    // adjoint of the flux capacitors
+    // prefetch targets: the stored rows of step t - 1 stream in with cp.async while step t is processed; the buffers
+    // rotate with s.st[0] / s.own[0] / s.aux[0] (no copy)
+    T* pre_st = q; q += 4 * NC;
+    T* pre_own = q; q += 2 * n_own;
+    T* pre_aux = q; q += AUX;
     T* pub = q; q += (size_t)L * 6;            // [L][2 sides][3] published (d green r, d green u, d signal)
     T* pubm = q; q += (size_t)ML * 5;          // [ML] (d signal prev, curr, next, d leader p, d leader v)
     int* pubi = reinterpret_cast<int*>(q);     // [ML][4] prev lane, next lane, leader micro index, leader slot
@@ -516,17 +524,24 @@ __global__ void __launch_bounds__(HYB_THREADS_MAX) hyb_rollout_bwd_kernel(HybArg
                 for (int k = 0; k < 3; k++) GV[k * ML * cap + c] = (occ && ga) ? ga[k * ML * cap + c] : T(0);
             }
         }
+#define DHTS_HYB_PREFETCH(TT)                                                                                          \
+        {                                                                                                              \
+            const T* h_ = hist + ((size_t)(TT) * n.R + b) * 4 * NC;                                                    \
+            for (int c = threadIdx.x; c < 4 * NC; c += blockDim.x) __pipeline_memcpy_async(pre_st + c, h_ + c, sizeof(T)); \
+            const T* oh_ = ownh + ((size_t)(TT) * n.R + b) * 2 * n_own;                                                \
+            for (int c = threadIdx.x; c < 2 * n_own; c += blockDim.x) __pipeline_memcpy_async(pre_own + c, oh_ + c, sizeof(T)); \
+            const T* ah_ = auxh + ((size_t)(TT) * n.R + b) * AUX;                                                      \
+            for (int c = threadIdx.x; c < AUX; c += blockDim.x) __pipeline_memcpy_async(pre_aux + c, ah_ + c, sizeof(T)); \
+            __pipeline_commit();                                                                                       \
+        }
+        if (n.T_steps > 0) DHTS_HYB_PREFETCH(n.T_steps - 1)
         for (int t = n.T_steps - 1; t >= 0; t--) {
-            __syncthreads();
-            {
-                const T* h = hist + ((size_t)t * n.R + b) * 4 * NC;
-                for (int c = threadIdx.x; c < 4 * NC; c += blockDim.x) s.st[0][c] = h[c];
-                const T* oh = ownh + ((size_t)t * n.R + b) * 2 * n_own;
-                for (int c = threadIdx.x; c < 2 * n_own; c += blockDim.x) s.own[0][c] = oh[c];
-                const T* ah = auxh + ((size_t)t * n.R + b) * AUX;
-                for (int c = threadIdx.x; c < AUX; c += blockDim.x) s.aux[0][c] = ah[c];
-            }
-            __syncthreads();
+            __pipeline_wait_prior(0);
+            __syncthreads();          // rows of step t have landed; the previous step's last readers of s.st[0] are done
+            { T* x_ = s.st[0]; s.st[0] = pre_st; pre_st = x_; x_ = s.own[0]; s.own[0] = pre_own; pre_own = x_;
+              x_ = s.aux[0]; s.aux[0] = pre_aux; pre_aux = x_; }
+            if (t > 0) DHTS_HYB_PREFETCH(t - 1)
+#undef DHTS_HYB_PREFETCH
             hyb_step<T, true>(a, s, b, t, 0, fl, ncol);          // replay: s.mid, s.log, s.kconst, s.aux[1]
             const T* cr = s.st[0]; const T* cy = cr + NC; const T* cu = cy + NC; const T* ce = cu + NC;
             const T* auxc = s.aux[0];
@@ -790,6 +805,7 @@ template <typename T> static size_t hyb_smem(const HybArgs<T>& a, bool adj) {
     if (adj) {
         el += 3 * NC + (size_t)a.NGL * (3 + a.MAXT);                       // mid, log.et
         el += 3 * NC + 2 * (size_t)a.n.n_own + 3 * ML * a.cap + a.NCAP + 6 * L + 5 * ML;
+        el += 4 * NC + 2 * (size_t)a.n.n_own + (size_t)a.ax.AUX;               // prefetch targets
         bytes += sizeof(int) * (4 * ML + 4 * (size_t)a.NGL);
     }
     bytes += sizeof(int) * L + sizeof(T);                                  // order
@@ -893,10 +909,19 @@ static HybArgs<T> hyb_args(const dhts_hyb_topology* tp, const T* dx, const T* la
         const int threads = dhts::hyb_threads(a.n.L);                                                                  \
         const size_t smem = dhts::hyb_smem<T>(a, true);                                                                \
         int grid = 1;                                                                                                  \
-        rc = dhts::hyb_launch_cfg(dhts::hyb_rollout_bwd_kernel<T>, smem, threads, R, &grid);                           \
-        if (rc) return rc;                                                                                             \
-        dhts::hyb_rollout_bwd_kernel<T><<<grid, threads, smem, (cudaStream_t)stream>>>(                                \
-            a, hist, own_hist, aux_hist, g_states, g_aux, g_r0, g_y0, g_u0, g_own0, g_sig, g_incoming, g_aux0, flags); \
+        if (threads <= 192) {                                                                                          \
+            rc = dhts::hyb_launch_cfg(dhts::hyb_rollout_bwd_kernel<T, 192>, smem, threads, R, &grid);                  \
+            if (rc) return rc;                                                                                         \
+            dhts::hyb_rollout_bwd_kernel<T, 192><<<grid, threads, smem, (cudaStream_t)stream>>>(                       \
+                a, hist, own_hist, aux_hist, g_states, g_aux, g_r0, g_y0, g_u0, g_own0, g_sig, g_incoming, g_aux0,     \
+                flags);                                                                                                \
+        } else {                                                                                                       \
+            rc = dhts::hyb_launch_cfg(dhts::hyb_rollout_bwd_kernel<T, dhts::HYB_THREADS_MAX>, smem, threads, R, &grid); \
+            if (rc) return rc;                                                                                         \
+            dhts::hyb_rollout_bwd_kernel<T, dhts::HYB_THREADS_MAX><<<grid, threads, smem, (cudaStream_t)stream>>>(     \
+                a, hist, own_hist, aux_hist, g_states, g_aux, g_r0, g_y0, g_u0, g_own0, g_sig, g_incoming, g_aux0,     \
+                flags);                                                                                                \
+        }                                                                                                              \
         return cudaGetLastError() == cudaSuccess ? DHTS_OK : DHTS_ERR_CUDA;                                            \
     }
 
