@@ -183,6 +183,7 @@ template <typename T> struct HybSm {
     T* mid;       // adjoint kernel: (r, y, u) x NC between update and conversions
     ConvLog<T> log;
     int* order;   // [L] thread -> lane assignment: macro lanes by decreasing number of cells, then the micro lanes
+    int* walk;    // [NGL][6] lookups of the conversion walk of the current step (lane, kind, next / micro index, capacitor, ...)
 };
 
 // Lanes sorted (stably) so that the threads of a warp do the same kind of work: macro lanes of equal length together,
@@ -301,6 +302,23 @@ __device__ __forceinline__ void hyb_step(const HybArgs<T>& a, const HybSm<T>& s,
             }
         }
     }
+    // ---- phase 2a: the table lookups of the conversion walk, one thread per group lane.  The walk itself is serial
+    // (lanes of a group in id order, one thread per group); from global memory each of its links -- group -> lane ->
+    // kind -> route -> capacitor -> micro index -- is an L2 round trip, which made it half of a step's latency
+    for (int gi = threadIdx.x; gi < a.NGL; gi += blockDim.x) {
+        const int l = a.grp_lane[gi];
+        int* w = s.walk + gi * 6;
+        w[0] = l; w[1] = n.kind[l]; w[2] = -1; w[3] = -1; w[4] = -1; w[5] = n.cell_off[l + 1] - 1;
+        if (w[1] == 0) {
+            const int nx = rt ? rt[L + l] : -1;
+            if (nx >= 0 && n.kind[nx] == 1) {
+                int k = -1;
+                for (int q = a.cap_off[l]; q < a.cap_off[l + 1]; q++) if (a.cap_lane[q] == nx) k = q;
+                w[2] = nx; w[3] = k; w[4] = a.mic_of[nx];
+            }
+        } else
+            w[2] = a.mic_of[l];
+    }
     if (bad) fl |= FLAG_CFL;
     if (bad_route) fl |= FLAG_ROUTE;
     __syncthreads();
@@ -312,18 +330,18 @@ __device__ __forceinline__ void hyb_step(const HybArgs<T>& a, const HybSm<T>& s,
     const T vlen = a.idm.len;
     for (int g = threadIdx.x; g < a.NG; g += blockDim.x) {
         for (int gi = a.grp_off[g]; gi < a.grp_off[g + 1]; gi++) {
-            const int l = a.grp_lane[gi];
+            const int* w = s.walk + gi * 6;
+            const int l = w[0];
             int ev = EV_NONE, e1 = 0, e2 = 0, e3 = 0;
-            if (n.kind[l] == 0) {                                                // conversion_macro
-                const int nx = rt ? rt[L + l] : -1;
-                if (nx >= 0 && n.kind[nx] == 1) {
-                    int k = -1;
-                    for (int q = a.cap_off[l]; q < a.cap_off[l + 1]; q++) if (a.cap_lane[q] == nx) k = q;
+            if (w[1] == 0) {                                                     // conversion_macro
+                const int nx = w[2];
+                if (nx >= 0) {
+                    const int k = w[3];
                     if (k >= 0) {                                                 // macro_to_micro, conversion.py:15-73
-                        const int c = n.cell_off[l + 1] - 1;
+                        const int c = w[5];
                         const T rl = nr[c], ul = nu[c];
                         const T flux = auxn[x.CAP + k] + rl * ul * n.dt;
-                        const int m2 = a.mic_of[nx];
+                        const int m2 = w[4];
                         const int f2 = (int)auxn[x.FRONT + m2], n2 = (int)auxn[x.CNT + m2];
                         const T space = n2 > 0 ? auxn[x.P + m2 * a.cap + (f2 + n2 - 1) % a.cap] - vlen * T(0.5) : a.lane_len[nx];
                         ev = EV_CAP; e2 = k;
@@ -344,7 +362,7 @@ __device__ __forceinline__ void hyb_step(const HybArgs<T>& a, const HybSm<T>& s,
                     }
                 }
             } else {                                                             // conversion_micro
-                const int m = a.mic_of[l];
+                const int m = w[2];
                 const int f = (int)auxn[x.FRONT + m], cnt = (int)auxn[x.CNT + m];
                 if (cnt > 0) {
                     const int o = m * a.cap + f;
@@ -416,6 +434,7 @@ template <typename T> __device__ __forceinline__ HybSm<T> hyb_carve(const HybArg
         s.log.et = q; q += (size_t)a.NGL * (3 + a.MAXT);
     }
     s.order = reinterpret_cast<int*>(q); q += ((size_t)a.n.L * sizeof(int) + sizeof(T) - 1) / sizeof(T);
+    s.walk = reinterpret_cast<int*>(q); q += ((size_t)a.NGL * 6 * sizeof(int) + sizeof(T) - 1) / sizeof(T);
     extra = q;
     return s;
 }
@@ -551,12 +570,14 @@ __global__ void __launch_bounds__(TMAX, TMAX <= 192 ? 2 : 1) hyb_rollout_bwd_ker
             // ---- R1: conversions reversed, last lane of each group first
             for (int g = threadIdx.x; g < a.NG; g += blockDim.x) {
                 for (int gi = a.grp_off[g + 1] - 1; gi >= a.grp_off[g]; gi--) {
-                    const int l = a.grp_lane[gi];
                     const int* e = s.log.ei + gi * 4;
-                    const T* et = s.log.et + gi * (3 + a.MAXT);
                     const int ev = e[0];
+                    if (ev == EV_NONE) continue;
+                    const int* w = s.walk + gi * 6;                    // lookups of the replayed step (hyb_step, phase 2a)
+                    const int l = w[0];
+                    const T* et = s.log.et + gi * (3 + a.MAXT);
                     if (ev == EV_CAP || ev == EV_SPAWN) {
-                        const int k = e[2], c = n.cell_off[l + 1] - 1;
+                        const int k = e[2], c = w[5];
                         const T rl = et[0], ul = et[1];
                         T gf = GC[k], gvn = T(0);
                         if (ev == EV_SPAWN) {
@@ -567,13 +588,13 @@ __global__ void __launch_bounds__(TMAX, TMAX <= 192 ? 2 : 1) hyb_rollout_bwd_ker
                         GC[k] = gf;
                         G[c] += gf * ul * n.dt; G[2 * NC + c] += gf * rl * n.dt + gvn;
                     } else if (ev == EV_DROP) {
-                        const int o = a.mic_of[l] * cap + e[1];
+                        const int o = w[2] * cap + e[1];
                         GV[o] = T(0); GV[ML * cap + o] = T(0); GV[2 * ML * cap + o] = T(0);
                     } else if (ev == EV_MOVE) {
-                        const int o = a.mic_of[l] * cap + e[1], o2 = e[2] * cap + e[3];
+                        const int o = w[2] * cap + e[1], o2 = e[2] * cap + e[3];
                         for (int k = 0; k < 3; k++) { GV[k * ML * cap + o] = GV[k * ML * cap + o2]; GV[k * ML * cap + o2] = T(0); }
                     } else if (ev == EV_ABSORB) {
-                        const int o = a.mic_of[l] * cap + e[1], nx = e[2], nt = e[3] < a.MAXT ? e[3] : a.MAXT;
+                        const int o = w[2] * cap + e[1], nx = e[2], nt = e[3] < a.MAXT ? e[3] : a.MAXT;
                         const int c0 = n.cell_off[nx];
                         const T dxn = n.dx[nx], ph = et[0], spd = et[1], ah = et[2];
                         const T v_hd = ph - a.lane_len[l], v_tl = v_hd - vlen;
@@ -809,6 +830,7 @@ template <typename T> static size_t hyb_smem(const HybArgs<T>& a, bool adj) {
         bytes += sizeof(int) * (4 * ML + 4 * (size_t)a.NGL);
     }
     bytes += sizeof(int) * L + sizeof(T);                                  // order
+    bytes += sizeof(int) * 6 * (size_t)a.NGL + sizeof(T);                  // walk
     return sizeof(T) * el + bytes + 32;
 }
 
