@@ -184,6 +184,8 @@ template <typename T> struct HybSm {
     ConvLog<T> log;
     int* order;   // [L] thread -> lane assignment: macro lanes by decreasing number of cells, then the micro lanes
     int* walk;    // [NGL][6] lookups of the conversion walk of the current step (lane, kind, next / micro index, capacitor, ...)
+    int* goff;    // [NG+1] group offsets (copy of grp_off)
+    T* walkT;     // [NGL] length of the lane the walk asks about (macro: the micro successor; micro: the lane itself)
 };
 
 // Lanes sorted (stably) so that the threads of a warp do the same kind of work: macro lanes of equal length together,
@@ -316,9 +318,13 @@ __device__ __forceinline__ void hyb_step(const HybArgs<T>& a, const HybSm<T>& s,
                 for (int q = a.cap_off[l]; q < a.cap_off[l + 1]; q++) if (a.cap_lane[q] == nx) k = q;
                 w[2] = nx; w[3] = k; w[4] = a.mic_of[nx];
             }
-        } else
+            s.walkT[gi] = nx >= 0 ? a.lane_len[nx] : T(0);
+        } else {
             w[2] = a.mic_of[l];
+            s.walkT[gi] = a.lane_len[l];
+        }
     }
+    for (int g = threadIdx.x; g <= a.NG; g += blockDim.x) s.goff[g] = a.grp_off[g];
     if (bad) fl |= FLAG_CFL;
     if (bad_route) fl |= FLAG_ROUTE;
     __syncthreads();
@@ -329,7 +335,7 @@ __device__ __forceinline__ void hyb_step(const HybArgs<T>& a, const HybSm<T>& s,
     // ---- phase 2: conversions, one thread per group, lanes in id order (road_network.py:113-173)
     const T vlen = a.idm.len;
     for (int g = threadIdx.x; g < a.NG; g += blockDim.x) {
-        for (int gi = a.grp_off[g]; gi < a.grp_off[g + 1]; gi++) {
+        for (int gi = s.goff[g]; gi < s.goff[g + 1]; gi++) {
             const int* w = s.walk + gi * 6;
             const int l = w[0];
             int ev = EV_NONE, e1 = 0, e2 = 0, e3 = 0;
@@ -343,7 +349,7 @@ __device__ __forceinline__ void hyb_step(const HybArgs<T>& a, const HybSm<T>& s,
                         const T flux = auxn[x.CAP + k] + rl * ul * n.dt;
                         const int m2 = w[4];
                         const int f2 = (int)auxn[x.FRONT + m2], n2 = (int)auxn[x.CNT + m2];
-                        const T space = n2 > 0 ? auxn[x.P + m2 * a.cap + (f2 + n2 - 1) % a.cap] - vlen * T(0.5) : a.lane_len[nx];
+                        const T space = n2 > 0 ? auxn[x.P + m2 * a.cap + (f2 + n2 - 1) % a.cap] - vlen * T(0.5) : s.walkT[gi];
                         ev = EV_CAP; e2 = k;
                         if (REC) { s.log.et[gi * (3 + a.MAXT)] = rl; s.log.et[gi * (3 + a.MAXT) + 1] = ul; }
                         if (flux >= vlen && space >= vlen) {
@@ -369,7 +375,7 @@ __device__ __forceinline__ void hyb_step(const HybArgs<T>& a, const HybSm<T>& s,
                     const T ph = auxn[x.P + o], vh = auxn[x.V + o], ah = auxn[x.A + o];
                     const int rid = (int)auxn[x.RID + o], cur = (int)auxn[x.CUR + o];
                     const int nx = route_at(a, rid, cur + 1);
-                    const T len = a.lane_len[l];
+                    const T len = s.walkT[gi];
                     bool pop = false;
                     if (nx < 0) { pop = ph >= len; if (pop) ev = EV_DROP; }       // micro_to_none, :202-215
                     else if (n.kind[nx] == 0) {                                   // micro_to_macro, :75-171
@@ -435,6 +441,8 @@ template <typename T> __device__ __forceinline__ HybSm<T> hyb_carve(const HybArg
     }
     s.order = reinterpret_cast<int*>(q); q += ((size_t)a.n.L * sizeof(int) + sizeof(T) - 1) / sizeof(T);
     s.walk = reinterpret_cast<int*>(q); q += ((size_t)a.NGL * 6 * sizeof(int) + sizeof(T) - 1) / sizeof(T);
+    s.goff = reinterpret_cast<int*>(q); q += ((size_t)(a.NG + 1) * sizeof(int) + sizeof(T) - 1) / sizeof(T);
+    s.walkT = q; q += a.NGL;
     extra = q;
     return s;
 }
@@ -569,7 +577,7 @@ __global__ void __launch_bounds__(TMAX, TMAX <= 192 ? 2 : 1) hyb_rollout_bwd_ker
             const T* inc_t = n.incoming ? n.incoming + ((size_t)b * n.T_steps + t) * L : nullptr;
             // ---- R1: conversions reversed, last lane of each group first
             for (int g = threadIdx.x; g < a.NG; g += blockDim.x) {
-                for (int gi = a.grp_off[g + 1] - 1; gi >= a.grp_off[g]; gi--) {
+                for (int gi = s.goff[g + 1] - 1; gi >= s.goff[g]; gi--) {
                     const int* e = s.log.ei + gi * 4;
                     const int ev = e[0];
                     if (ev == EV_NONE) continue;
@@ -831,6 +839,7 @@ template <typename T> static size_t hyb_smem(const HybArgs<T>& a, bool adj) {
     }
     bytes += sizeof(int) * L + sizeof(T);                                  // order
     bytes += sizeof(int) * 6 * (size_t)a.NGL + sizeof(T);                  // walk
+    bytes += sizeof(int) * (size_t)(a.NG + 1) + sizeof(T); el += a.NGL;   // goff, walkT
     return sizeof(T) * el + bytes + 32;
 }
 
