@@ -271,7 +271,7 @@ __device__ __forceinline__ bool chunk_fwd_step(T* r, T* y, const T* us, bool fir
     for (int c = 0; c < C; c++) anyvac |= maybe_vac(r[c]);
     T f0[2], fpr = T(0), fpy = T(0);
     bool bad;
-    if (anyvac) bad = chunk_fwd_sweep<T, C, STORED, CHECK, true>(r, y, us, last, L, k, dt, f0, fpr, fpy, okL);
+    if (__builtin_expect(anyvac, 0)) bad = chunk_fwd_sweep<T, C, STORED, CHECK, true>(r, y, us, last, L, k, dt, f0, fpr, fpy, okL);
     else bad = chunk_fwd_sweep<T, C, STORED, CHECK, false>(r, y, us, last, L, k, dt, f0, fpr, fpy, okL);
     T fR[2];
     from_right<T, 2>(f0, fR, boxR, warp, nwarp, lane);
@@ -427,7 +427,7 @@ __device__ __forceinline__ bool chunk_adj_step(const T* r, const T* y, const T* 
 #pragma unroll
     for (int c = 0; c < C - 1; c++) anyvac |= maybe_vac(r[c]);
     bool nan;
-    if (anyvac) nan = chunk_adj_sweep<T, C, STORED, true>(r, y, us, gr, gy, last, L, gLr, gLy, k, a0, bpr, bpy);
+    if (__builtin_expect(anyvac, 0)) nan = chunk_adj_sweep<T, C, STORED, true>(r, y, us, gr, gy, last, L, gLr, gLy, k, a0, bpr, bpy);
     else nan = chunk_adj_sweep<T, C, STORED, false>(r, y, us, gr, gy, last, L, gLr, gLy, k, a0, bpr, bpy);
     T aR[2];
     from_right<T, 2>(a0, aR, boxR, warp, nwarp, lane);

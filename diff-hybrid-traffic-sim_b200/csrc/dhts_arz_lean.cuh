@@ -119,9 +119,12 @@ __device__ __forceinline__ Tree<T> case_tree(T Lr, T Lus, T Lsq, T Lw, T Rr, T R
     const bool m_neg = fma(-k.hum, rootm, Rus) <= T(0);            // lambda_0(Q_M) <= 0
     t.sc = fma(k.umax, Lsq, Lus);                                  // Q_C: r_c = q^2, u_c = sc / 3
     t.q = t.sc * k.inv15;
-    const bool tailL = shock ? (t.fd >= T(0)) : l0;
-    t.isL = vacL || (vacR ? l0 : (same || tailL));
-    t.isM = !t.isL && !vacR && (shock || (rare && m_neg));
+    // bitwise, not short-circuit: `||` / `&&` made the compiler branch around the lambda_0(Q_M) chain (a divergent
+    // 10-instruction block per interface that also splits the sweep into small basic blocks)
+    const bool fd_ok = t.fd >= T(0);
+    const bool tailL = (shock & fd_ok) | (!shock & l0);
+    t.isL = vacL | (vacR ? l0 : (same | tailL));
+    t.isM = !t.isL & !vacR & (shock | (rare & m_neg));
     return t;
 }
 
