@@ -243,7 +243,9 @@ __device__ __forceinline__ bool chunk_fwd_sweep(T* r, T* y, const T* us, const F
         fflux<T, VAC>(L, cur.r, cur.us, k, fr, fy);
         if (CHECK) {
             const bool okR = cell_speed_ok(cur.us, cur.w, k);
-            if (!okL || !okR) bad |= cfl_exact_bad(L.r, L.us, L.sq, L.w, cur.r, cur.us, k, dt);   // never in a valid run
+            // never in a valid run; the vote makes the branch warp-uniform (no reconvergence bookkeeping around it): every
+            // lane then evaluates the exact test, which is what the flag means anyway
+            if (__any_sync(FULL, !okL | !okR)) bad |= cfl_exact_bad(L.r, L.us, L.sq, L.w, cur.r, cur.us, k, dt);
             okL = okR;
         }
         if (c == 0) { f0[0] = fr; f0[1] = fy; }
@@ -271,6 +273,7 @@ __device__ __forceinline__ bool chunk_fwd_step(T* r, T* y, const T* us, bool fir
     for (int c = 0; c < C; c++) anyvac |= maybe_vac(r[c]);
     T f0[2], fpr = T(0), fpy = T(0);
     bool bad;
+    anyvac = __any_sync(FULL, anyvac);            // one variant per warp (a mixed warp would run both, one after the other)
     if (__builtin_expect(anyvac, 0)) bad = chunk_fwd_sweep<T, C, STORED, CHECK, true>(r, y, us, last, L, k, dt, f0, fpr, fpy, okL);
     else bad = chunk_fwd_sweep<T, C, STORED, CHECK, false>(r, y, us, last, L, k, dt, f0, fpr, fpy, okL);
     T fR[2];
@@ -427,6 +430,7 @@ __device__ __forceinline__ bool chunk_adj_step(const T* r, const T* y, const T* 
 #pragma unroll
     for (int c = 0; c < C - 1; c++) anyvac |= maybe_vac(r[c]);
     bool nan;
+    anyvac = __any_sync(FULL, anyvac);            // one variant per warp
     if (__builtin_expect(anyvac, 0)) nan = chunk_adj_sweep<T, C, STORED, true>(r, y, us, gr, gy, last, L, gLr, gLy, k, a0, bpr, bpy);
     else nan = chunk_adj_sweep<T, C, STORED, false>(r, y, us, gr, gy, last, L, gLr, gLy, k, a0, bpr, bpy);
     T aR[2];
