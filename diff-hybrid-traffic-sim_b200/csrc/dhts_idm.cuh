@@ -34,7 +34,7 @@ __device__ __forceinline__ IdmEval<T> idm_eval(T v, const IdmPar<T>& k, T dp_raw
     e.clip_s = s < T(0);
     s = t_max(s, T(0));
     T q = v * k.v_t_inv; q = q * q;
-    T sr = s / dp;
+    T sr = s * f_rcp(dp);              // dp >= 1e-5: branch-free reciprocal (<= 1 ulp) instead of the IEEE division's slow-path call
     T acc = k.a_max * (T(1) - q * q - sr * sr);
     T lim = -v * inv_dt;
     e.clip_acc = acc < lim;
@@ -49,7 +49,7 @@ template <typename T>
 __device__ __forceinline__ void idm_jac(T v, const IdmPar<T>& k, T dp_raw, T dv_raw, const IdmEval<T>& e, T dt,
                                         T& E10, T& E11, T& L10, T& L11) {
     if (e.clip_acc) { E10 = T(0); E11 = T(0); L10 = T(0); L11 = T(0); return; }
-    T idp = T(1) / dp_raw;
+    T idp = f_rcp(dp_raw);             // raw gap (dmicro_lane.py:97); a zero gap gives a non-finite Jacobian (the reference raises), flagged as NaN gradient
     T sd2 = e.s * idp * idp;          // s / dp^2
     T sd3 = e.s * sd2 * idp;          // s^2 / dp^3
     L10 = dt * (T(2) * k.a_max * sd3);
