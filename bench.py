@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--ckpt-every", type=int, default=0,
                     help="ARZ checkpoint interval; 0 = auto: store every state (no recompute in the adjoint) and walk "
                          "the lanes in chunks that fit the free HBM, else 32 with segment recompute")
-    ap.add_argument("--idm-ckpt-every", type=int, default=32)
+    ap.add_argument("--idm-ckpt-every", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-net", action="store_true", help="skip the secondary connected-network (ITSCP) measurement")

@@ -87,12 +87,12 @@ template <typename T> struct Cell {
 
 // u_eq(r) = u_max (1 - (max(r,0)+eps)^gamma)                    _arz.py:133-138
 template <typename T> __device__ __forceinline__ T u_eq(T r, T umax) {
-    return umax * (T(1) - t_sqrt(t_max(r, T(0)) + DHTS_EPS));
+    return umax * (T(1) - f_sqrt_pos(t_max(r, T(0)) + DHTS_EPS));      // argument >= eps: branch-free sqrt (<= 1 ulp)
 }
 // compute_u(r, y)                                               _arz.py:126-131
 template <typename T> __device__ __forceinline__ T compute_u(T r, T y, T umax) {
     T rc = t_max(r, DHTS_EPS);
-    return y / rc + umax * (T(1) - t_sqrt(rc + DHTS_EPS));
+    return y * f_rcp(rc) + umax * (T(1) - f_sqrt_pos(rc + DHTS_EPS));  // rc >= eps: no IEEE division / sqrt slow paths
 }
 
 // Record of a cell whose (u, u_eq) follow set_r_y (_arz.py:88-92), i.e. every
@@ -245,9 +245,9 @@ __device__ __forceinline__ void riemann_adj(const Cell<T>& L, const Cell<T>& R, 
 // y/max(r,eps) + u_max (1 - (max(r,eps)+eps)^gamma).
 template <typename T> __device__ __forceinline__ void du_dry(T r, T y, T umax, T& du_dr, T& du_dy) {
     if (r >= DHTS_EPS) {
-        T ri = T(1) / r;
+        T ri = f_rcp(r);
         du_dy = ri;
-        du_dr = -y * ri * ri - T(0.5) * umax / t_sqrt(r + DHTS_EPS);
+        du_dr = -y * ri * ri - T(0.5) * umax * f_rsqrt(r + DHTS_EPS);
     } else {
         du_dy = T(1) / DHTS_EPS;
         du_dr = T(0);

@@ -30,12 +30,12 @@ template <typename T> struct NetArgs {
     const int* kind;              // [L] 0 macro, 1 micro, or null (all macro)
 };
 
-template <typename T> __device__ __forceinline__ T sigm(T x) { return T(1) / (T(1) + exp(-x)); }
+template <typename T> __device__ __forceinline__ T sigm(T x) { return f_rcp(T(1) + exp(-x)); }      // |x| <= 16: 1 + e^-x in [1, 9e6]
 
 
 // u_eq'(r) as autograd differentiates ARZ.compute_u_eq on a tensor (_arz.py:133-138: max(r, 0.) keeps r when r >= 0)
 template <typename T> __device__ __forceinline__ T u_eq_true_prime(T r, T umax) {
-    return (r >= T(0)) ? T(-0.5) * umax / t_sqrt(r + DHTS_EPS) : T(0);
+    return (r >= T(0)) ? T(-0.5) * umax * f_rsqrt(r + DHTS_EPS) : T(0);
 }
 
 template <typename T> struct Side {
