@@ -407,7 +407,6 @@ __device__ __forceinline__ bool chunk_adj_sweep(const T* r, const T* y, const T*
         else {
             gr[c - 1] = fma(k.cc, ar + bpr, gLr);
             gy[c - 1] = fma(k.cc, ay + bpy, gLy);
-            nan |= t_isnan(gr[c - 1]) || t_isnan(gy[c - 1]);
         }
         bpr = br; bpy = by; L = cur; gLr = gcr; gLy = gcy;
     }
@@ -444,7 +443,6 @@ __device__ __forceinline__ bool chunk_adj_step(const T* r, const T* y, const T* 
     if (first_chunk) { accL[0] = fma(k.cc, a0[0], accL[0]); accL[1] = fma(k.cc, a0[1], accL[1]); }
     gr[C - 1] = fma(k.cc, aR[0] + bpr, gLr);
     gy[C - 1] = fma(k.cc, aR[1] + bpy, gLy);
-    nan |= t_isnan(gr[C - 1]) || t_isnan(gy[C - 1]);
     return nan;
 }
 
@@ -604,6 +602,10 @@ __global__ void __launch_bounds__(1024 / (C < 4 ? C : 4), MB) arz_rollout_bwd_re
                 }
             }
         }
+        // NaN test of the gradients (dmacro_lane.py:308 asserts after every backward step): every step adds to the OLD adjoint
+        // of the same cell, so a NaN never leaves a cell once it is there and one test of the final adjoint sees them all
+#pragma unroll
+        for (int c = 0; c < C; c++) nan |= t_isnan(gr[c]) || t_isnan(gy[c]);
         bad |= nan && active;
         if (active) {
             store_chunk<T, C>(g_r0 + off, gr); store_chunk<T, C>(g_y0 + off, gy);
