@@ -281,3 +281,32 @@ def test_rollout_plan_fits_memory(dev):
     assert F.arz_rollout_plan(100, 64, 10, torch.float64, dev) == (100, 1)
     chunk, K = F.arz_rollout_plan(4096, 1024, 10 ** 7, torch.float64, dev)        # nothing fits: sparse checkpoints
     assert K == 32 and chunk >= 1
+
+
+@pytest.mark.parametrize("ckpt_every,N", [(1, 1024), (16, 1024), (1, 40)])
+def test_nan_gradient_flag_maps_to_assertion(dev, ckpt_every, N):
+    """A NaN that enters the adjoint (here: through the terminal adjoint of ONE cell) stays in that cell through every step,
+    so the single test of the final adjoint raises the reference's NaN assert (dmacro_lane.py:308); without a NaN the flag
+    stays clear.  Covers the TMA-ring, the recompute and the small-lane paths of the adjoint kernel."""
+    from dhts_b200 import Flags, functional as F
+    from dhts_b200._lib import FLAG_NAN_GRAD
+    rng = np.random.default_rng(5)
+    B, T = 3, 40
+    r0 = T64(rng.uniform(0.1, 0.9, (B, N)), dev); u0 = T64(rng.uniform(0, 30, (B, N)), dev)
+    gr = T64(rng.uniform(0.1, 0.9, (B, 2)), dev); gu = T64(rng.uniform(0, 30, (B, 2)), dev)
+    for poison in (False, True):
+        tr = r0.clone().requires_grad_()
+        flags = Flags(dev)
+        rT, yT, uT = F.arz_rollout(tr, u0, gr, gu, 5.0, 30.0, 0.01, T, ckpt_every=ckpt_every, flags=flags)
+        w = torch.ones_like(rT)
+        if poison:
+            w[1, N // 2] = float("nan")
+        (rT * w).sum().backward()
+        bits, _ = flags.read()
+        assert bool(bits & FLAG_NAN_GRAD) == poison
+        assert bool(torch.isnan(tr.grad[1]).any()) == poison and not bool(torch.isnan(tr.grad[0]).any())
+        if poison:
+            with pytest.raises(AssertionError):
+                flags.check()
+        else:
+            flags.check()
