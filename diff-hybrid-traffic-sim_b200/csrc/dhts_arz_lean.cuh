@@ -219,7 +219,7 @@ __device__ __forceinline__ void aflux(const ARec<T>& L, const ARec<T>& R, T wr, 
     const T y0 = r0 * g;
     // flux_prime at Q0 with r clamped at eps
     const bool big = r0 >= DHTS_EPS;
-    const T inv_sq = big ? f_rcp(t_max(rootr, T(1e-30))) : DHTS_RSQRT_EPS;
+    const T inv_sq = big ? f_rcp(rootr) : DHTS_RSQRT_EPS;      // rootr >= sqrt(eps) where it is selected; a non-finite value in the other arm is discarded
     const T rr = big ? r0 : DHTS_EPS;
     const T ueqp0 = -k.hum * inv_sq;
     const T yr = y0 * (inv_sq * inv_sq);
