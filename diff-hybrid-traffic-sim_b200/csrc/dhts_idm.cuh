@@ -48,21 +48,21 @@ __device__ __forceinline__ IdmEval<T> idm_eval(T v, const IdmPar<T>& k, T dp_raw
 template <typename T>
 __device__ __forceinline__ void idm_jac(T v, const IdmPar<T>& k, T dp_raw, T dv_raw, const IdmEval<T>& e, T dt,
                                         T& E10, T& E11, T& L10, T& L11) {
-    if (e.clip_acc) { E10 = T(0); E11 = T(0); L10 = T(0); L11 = T(0); return; }
+    // Branch-free: the two clips differ per vehicle, so branches here diverge in every warp.  With s* clipped e.s is 0, hence
+    // s / dp^2 = 0 and the general expressions reduce to the clipped ones of didm.py:38-56,84-102 (E11 = 1 + dt a_max t1, L11 = 0);
+    // the acceleration clip zeroes both second rows.
     T idp = f_rcp(dp_raw);             // raw gap (dmicro_lane.py:97); a zero gap gives a non-finite Jacobian (the reference raises), flagged as NaN gradient
     T sd2 = e.s * idp * idp;          // s / dp^2
     T sd3 = e.s * sd2 * idp;          // s^2 / dp^3
-    L10 = dt * (T(2) * k.a_max * sd3);
-    E10 = -L10;
+    T l10 = dt * (T(2) * k.a_max * sd3);
     T vt2 = k.v_t_inv * k.v_t_inv;
     T t1 = T(-4) * (v * v * v) * (vt2 * vt2);
-    if (e.clip_s) {
-        E11 = T(1) + dt * k.a_max * t1;
-        L11 = dt * k.a_max * (T(-2) * sd2);
-    } else {
-        E11 = T(1) + dt * k.a_max * (t1 - T(2) * sd2 * (k.tp + (v + dv_raw) * k.sab2_inv));
-        L11 = dt * k.a_max * (T(-2) * sd2 * (-v * k.sab2_inv));
-    }
+    T e11 = T(1) + dt * k.a_max * (t1 - T(2) * sd2 * (k.tp + (v + dv_raw) * k.sab2_inv));
+    T l11 = dt * k.a_max * (T(-2) * sd2 * (-v * k.sab2_inv));
+    L10 = e.clip_acc ? T(0) : l10;
+    E10 = e.clip_acc ? T(0) : -l10;
+    E11 = e.clip_acc ? T(0) : e11;
+    L11 = e.clip_acc ? T(0) : l11;
 }
 
 }  // namespace dhts
