@@ -103,6 +103,7 @@ class ItscpGrid:
                             con = index[(row + dr, col + dc, there, None, not app, k)]
                             links.append((con, cur) if app else (cur, con))
         self.lanes, self.links = lanes, links
+        self._sig_tables = {}
         self.L = len(lanes)
         self.num_cell = [max(1, math.ceil(l.length / self.cell_length)) for l in lanes]     # MacroLane.__init__, _macro_lane.py:38-44
         self.dx = [l.length / c for l, c in zip(lanes, self.num_cell)]
@@ -122,24 +123,29 @@ class ItscpGrid:
         R, A = action.shape
         n2 = self.num_intersection ** 2
         n_phase = A // n2
-        t = torch.arange(num_frames, device=action.device)
+        dev = action.device
+        key = (str(dev), action.dtype)
+        tab = self._sig_tables.get(key)
+        if tab is None:      # approaching access lanes: their lane index, intersection cell and sign (+1 west / east, -1 north / south)
+            lanes = [(l, i.row * self.num_intersection + i.col, 1.0 if i.loc in ("west", "east") else -1.0)
+                     for l, i in enumerate(self.lanes) if i.loc != "mid" and i.approaching]
+            tab = (torch.tensor([x[0] for x in lanes], dtype=torch.long, device=dev),
+                   torch.tensor([x[1] for x in lanes], dtype=torch.long, device=dev),
+                   torch.tensor([x[2] for x in lanes], dtype=action.dtype, device=dev))
+            self._sig_tables[key] = tab
+        lane_idx, cell_idx, sign = tab
+        t = torch.arange(num_frames, device=dev)
         phase = torch.clamp(t // frames_per_signal, max=n_phase - 1)
         progress = torch.clamp((t % frames_per_signal).to(action.dtype) / frames_per_signal, max=1.0)
-        sig = torch.ones((R, num_frames, self.L), dtype=action.dtype, device=action.device)
-        cols = []
-        for l, info in enumerate(self.lanes):
-            if info.loc == "mid" or not info.approaching:
-                continue
-            a = action[:, phase * n2 + info.row * self.num_intersection + info.col]       # [R, T]
-            d = (a - progress) if info.loc in ("west", "east") else (progress - a)
+        sig = torch.ones((R, num_frames, self.L), dtype=action.dtype, device=dev)
+        if lane_idx.numel():
+            col = phase[:, None] * n2 + cell_idx[None, :]                        # [T, lanes] action column of every (frame, lane)
+            d = (action[:, col] - progress[None, :, None]) * sign                # a - progress (W/E) or progress - a (N/S)
             if soft:
-                s = torch.sigmoid(torch.clamp(d * 32.0, -16.0, 16.0))                      # dmath.sigmoid, operation.py:3-30
+                s = torch.sigmoid(torch.clamp(d * 32.0, -16.0, 16.0))            # dmath.sigmoid, operation.py:3-30
             else:
                 s = (d > 0).to(action.dtype)
-            cols.append((l, s))
-        if cols:
-            idx = torch.tensor([l for l, _ in cols], device=action.device)
-            sig = sig.index_copy(2, idx, torch.stack([s for _, s in cols], dim=2))
+            sig = sig.index_copy(2, lane_idx, s)
         return sig
 
 
