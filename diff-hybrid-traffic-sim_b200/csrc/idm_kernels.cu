@@ -157,10 +157,11 @@ __device__ __forceinline__ void lane_deltas(const WarpLane<T, VPT>& w, T head_dp
                                             T* dv) {
 #pragma unroll
     for (int m = 0; m < VPT; m++) {
-        T up_p = __shfl_down_sync(0xffffffffu, w.p[m], 1), up_v = __shfl_down_sync(0xffffffffu, w.v[m], 1);
-        T ed_p = __shfl_sync(0xffffffffu, w.p[m + 1 < VPT ? m + 1 : m], 0);
-        T ed_v = __shfl_sync(0xffffffffu, w.v[m + 1 < VPT ? m + 1 : m], 0);
-        T lp = (lane == 31) ? ed_p : up_p, lv = (lane == 31) ? ed_v : up_v;
+        // one rotation per value: lane i takes lane i+1's entry of this slot; lane 31 takes lane 0's entry of the NEXT slot,
+        // which lane 0 sends instead of its own (nobody reads lane 0's own entry in a shift by one)
+        const T sp_ = (lane == 0) ? w.p[m + 1 < VPT ? m + 1 : m] : w.p[m];
+        const T sv_ = (lane == 0) ? w.v[m + 1 < VPT ? m + 1 : m] : w.v[m];
+        const T lp = __shfl_sync(0xffffffffu, sp_, (lane + 1) & 31), lv = __shfl_sync(0xffffffffu, sv_, (lane + 1) & 31);
         if (w.head[m]) { dp[m] = head_dp; dv[m] = head_dv; }
         else { dp[m] = t_abs(lp - w.p[m]) - (w.lead_len[m] + w.k[m].len) * T(0.5); dv[m] = w.v[m] - lv; }
     }
@@ -265,16 +266,17 @@ idm_rollout_bwd_kernel(const T* __restrict__ ckpt, const T* __restrict__ params,
                 // follower (e-1) -> me: within a slot from lane-1, across slots from lane 31 of slot m-1
 #pragma unroll
                 for (int m = 0; m < VPT; m++) {
-                    T dn_p = __shfl_up_sync(0xffffffffu, cpv[m], 1), dn_v = __shfl_up_sync(0xffffffffu, cvv[m], 1);
-                    T ed_p = __shfl_sync(0xffffffffu, cpv[m > 0 ? m - 1 : 0], 31);
-                    T ed_v = __shfl_sync(0xffffffffu, cvv[m > 0 ? m - 1 : 0], 31);
-                    T fp = (lane == 0) ? (m > 0 ? ed_p : T(0)) : dn_p;
-                    T fv = (lane == 0) ? (m > 0 ? ed_v : T(0)) : dn_v;
+                    // one rotation per value (see lane_deltas): lane 31 sends the PREVIOUS slot's entry, which lane 0 needs
+                    const T sp_ = (lane == 31) ? (m > 0 ? cpv[m > 0 ? m - 1 : 0] : T(0)) : cpv[m];
+                    const T sv_ = (lane == 31) ? (m > 0 ? cvv[m > 0 ? m - 1 : 0] : T(0)) : cvv[m];
+                    const T fp = __shfl_sync(0xffffffffu, sp_, (lane + 31) & 31), fv = __shfl_sync(0xffffffffu, sv_, (lane + 31) & 31);
                     if (w.valid[m]) { gp[m] = np_[m] + fp; gv[m] = nv_[m] + fv; }
-                    bad |= t_isnan(gp[m]) || t_isnan(gv[m]);
                 }
             }
         }
+        // NaN test once, on the final adjoint: gp' = gp + ..., gv' = dt gp + E11 gv + ... keep a NaN in its vehicle for good
+#pragma unroll
+        for (int m = 0; m < VPT; m++) bad |= t_isnan(gp[m]) || t_isnan(gv[m]);
 #pragma unroll
         for (int m = 0; m < VPT; m++)
             if (w.valid[m]) { g_p0[o + m * 32 + lane] = gp[m]; g_v0[o + m * 32 + lane] = gv[m]; }
