@@ -135,3 +135,31 @@ def test_collisions_and_clips_vs_oracle(dev):
         tot += o["ncol"]
     bits, ncol = flags.read()
     assert tot > 0 and ncol == tot and bits & 4
+
+
+@pytest.mark.parametrize("n,K", [(64, 16), (20, 1), (130, 8)])
+def test_rollout_nan_gradient_flag(dev, n, K):
+    """A NaN in the terminal adjoint of one vehicle stays in that vehicle through every adjoint step, so the single test of
+    the final adjoint raises the NaN-gradient flag (the reference asserts per step, dmacro_lane.py:308 convention); clean
+    inputs leave it clear.  One-, two- and multi-slot warps."""
+    import dhts_b200
+    from dhts_b200 import functional as F
+    from dhts_b200._lib import FLAG_NAN_GRAD
+    rng = np.random.default_rng(n)
+    umax, dt, T, L = 30.0, 0.01, 40, 3
+    V = L * n
+    off = np.arange(L + 1) * n
+    p0 = np.concatenate([np.arange(n) * 20.0 + rng.uniform(0, 5, n) for _ in range(L)]); v0 = rng.uniform(9, 21, V)
+    par = np.stack([np.full(V, umax), np.full(V, 0.8 * umax), np.full(V, 0.9 * umax), np.full(V, 0.5), np.full(V, 0.1), np.full(V, 5.0)])
+    head = np.tile(np.array([[1000.0, 0.0]]), (L, 1))
+    for poison in (False, True):
+        tp = T64(p0, dev).requires_grad_()
+        flags = dhts_b200.Flags(dev)
+        pT, vT = F.idm_rollout(tp, T64(v0, dev), T64(par, dev), I32(off, dev), T64(head, dev), dt, T, ckpt_every=K, flags=flags)
+        w = torch.ones_like(pT)
+        if poison:
+            w[n + n // 2] = float("nan")
+        (pT * w).sum().backward()
+        bits, _ = flags.read()
+        assert bool(bits & FLAG_NAN_GRAD) == poison
+        assert bool(torch.isnan(tp.grad[n:2 * n]).any()) == poison and not bool(torch.isnan(tp.grad[:n]).any())
