@@ -52,6 +52,12 @@ extern "C" {
 
 int dhts_version(void);
 
+/* Measurement helper, not on the simulation path: enqueues `blocks` CTAs of 256 threads that each run 8
+ * independent chains of `iters` fp64 fused multiply-adds and store one value per thread into out[blocks*256].
+ * Returns the number of DFMA thread-instructions enqueued (-1 on error).  bench.py times it with CUDA events to
+ * put a MEASURED fp64 issue peak next to the HBM peak of MEASURED_PEAKS.json (`roofline_fp64`). */
+long long dhts_fp64_probe(double* out, int blocks, int iters, void* stream);
+
 /* ---------------------------------------------------------------- ARZ, one step
  * Forward half of dMacroForwardLayer (dmacro_lane.py:236-275 -> MacroLane.forward,
  * _macro_lane.py:83-146; Riemann solver model/macro/_arz.py:212-332).

@@ -1,9 +1,10 @@
 #!/usr/bin/env python
 """Condense `ncu -i X.ncu-rep --page raw --csv` into the per-kernel JSON summaries kept under profiles/,
-and (with --traffic) refresh profiles/traffic.json, which bench.py reads for `roofline.traffic`.
+and (with --mix) refresh profiles/kernel_mix.json, which bench.py reads for `roofline.traffic` (DRAM bytes per
+update) and `roofline_fp64` (fp64-pipe / total thread-instructions per update).
 
-    python scripts/ncu_summary.py gpurun_out/r1d_full_raw.csv profiles/r1d_rollout_ncu_summary.json \
-        --work "2368 lanes x 1024 cells x 64 steps" --cell-steps 155189248 --traffic
+    python scripts/ncu_summary.py gpurun_out/r2a_full_raw.csv profiles/r2a_rollout_ncu_summary.json \
+        --work "6560 lanes x 1024 cells x 256 steps" --cell-steps 1719664640 --vehicle-steps 268435456 --mix --suffix _k1
 """
 import argparse
 import csv
@@ -17,7 +18,10 @@ KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__thread_inst_executed_per_inst_executed.ratio",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
-        "sm__throughput.avg.pct_of_peak_sustained_elapsed"]
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__cycles_elapsed.avg", "sm__cycles_active.avg",
+        "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum.per_cycle_elapsed",
+        "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum.per_cycle_elapsed",
+        "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed"]
 SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 
 
@@ -26,7 +30,11 @@ def main():
     ap.add_argument("raw_csv"); ap.add_argument("out_json")
     ap.add_argument("--work", default=""); ap.add_argument("--command", default="")
     ap.add_argument("--cell-steps", type=float, default=0.0, help="cell-steps (or vehicle-steps) per ARZ launch")
+    ap.add_argument("--vehicle-steps", type=float, default=0.0, help="vehicle-steps per IDM launch")
     ap.add_argument("--traffic", action="store_true")
+    ap.add_argument("--mix", action="store_true", help="refresh profiles/kernel_mix.json")
+    ap.add_argument("--idm-suffix", default="", help="kernel_mix.json key suffix of the IDM kernels, e.g. _k16")
+    ap.add_argument("--sms", type=int, default=148)
     ap.add_argument("--suffix", default="", help="appended to the traffic.json keys, e.g. _k1 for the store-every-state mode")
     a = ap.parse_args()
     rows = list(csv.reader(open(a.raw_csv)))
@@ -49,6 +57,16 @@ def main():
         if a.cell_steps and "arz" in k["Kernel Name"]:
             k["thread_inst_per_cell_step"] = k["smsp__inst_executed.sum"] * 32 / a.cell_steps
             k["dram_bytes_per_cell_step"] = (k["dram__bytes_read.sum"] + k["dram__bytes_write.sum"]) / a.cell_steps
+        units_ = a.cell_steps if "arz" in k["Kernel Name"] else (a.vehicle_steps if "idm" in k["Kernel Name"] else 0.0)
+        if units_:
+            cyc = k.get("smsp__cycles_elapsed.avg", 0.0)
+            ar = sum(k.get("smsp__sass_thread_inst_executed_op_%s_pred_on.sum.per_cycle_elapsed" % o, 0.0) for o in ("dadd", "dfma", "dmul"))
+            k["thread_inst_per_update"] = k["smsp__inst_executed.sum"] * k.get("smsp__thread_inst_executed_per_inst_executed.ratio", 32.0) / units_
+            k["dram_bytes_per_update"] = (k["dram__bytes_read.sum"] + k["dram__bytes_write.sum"]) / units_
+            k["fp64_arith_inst_per_update"] = ar * cyc / units_                      # DADD + DFMA + DMUL thread-instructions
+            # everything the fp64 pipe executed (arithmetic + DSETP / conversions): pipe-active cycles x 16 lanes per SMSP x 4
+            k["fp64_pipe_inst_per_update"] = (k.get("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", 0.0) / 100.0
+                                              * k.get("sm__cycles_active.avg", 0.0) * 64.0 * a.sms / units_)
         out.append(k)
     json.dump({"command": a.command, "work": a.work, "kernels": out}, open(a.out_json, "w"), indent=1)
     if a.traffic:
@@ -63,6 +81,22 @@ def main():
                       "source": os.path.basename(a.out_json)}
             if a.cell_steps and "arz" in key:
                 t[key]["dram_bytes_per_cell_step"] = t[key]["dram_bytes_per_launch"] / a.cell_steps
+        json.dump(t, open(path, "w"), indent=1)
+    if a.mix:
+        path = os.path.join(os.path.dirname(a.out_json), "kernel_mix.json")
+        t = json.load(open(path)) if os.path.exists(path) else {}
+        for k in out:
+            name = re.match(r"void (\w+)<(\w+)", k["Kernel Name"])
+            if not name or "thread_inst_per_update" not in k:
+                continue
+            kern = name.group(1).replace("_reg_kernel", "").replace("_kernel", "")
+            key = kern + ("_f64" if name.group(2) == "double" else "_f32") + (a.suffix if "arz" in kern else a.idm_suffix)
+            t[key] = {m: k[m] for m in ("thread_inst_per_update", "dram_bytes_per_update", "fp64_arith_inst_per_update",
+                                        "fp64_pipe_inst_per_update")}
+            t[key].update(work=a.work, source=os.path.basename(a.out_json), registers=k.get("launch__registers_per_thread"),
+                          fp64_pipe_pct=k.get("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+                          issue_pct=k.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                          dram_pct=k.get("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"))
         json.dump(t, open(path, "w"), indent=1)
     print(json.dumps(out, indent=1)[:3000])
 

@@ -1,7 +1,10 @@
 """Size-independent properties at BASELINE.json's full per-GPU shapes (65536 lanes x 1024 cells; 4,194,304 vehicles
 in 65536 lanes), where the oracle cannot follow: lanes are independent, so results must be BITWISE invariant under
 sharding, lane permutation and the checkpoint interval, and a lane with zero loss weight must get an exactly zero
-gradient.  (Steps are kept at 96 so the test stays in seconds; the time loop is the same code for any T.)"""
+gradient.  (Steps are kept at 96 so the test stays in seconds; the time loop is the same code for any T.)
+The base run uses ckpt_every = 1 -- every state stored, TMA staging ring forward, TMA ring adjoint: the mode
+bench.py times (103 GB of stored states for the 65536 lanes x 96 steps here); the oracle comparison of that mode at
+the full T = 1000 is tests/test_headline_gpu.py."""
 import pytest
 import torch
 
@@ -27,23 +30,23 @@ def test_arz_full_batch_invariances(dev):
     w = torch.randn((B, N), generator=g, dtype=torch.float64, device=dev)
     w[1::2] = 0.0                                            # odd lanes carry no loss
     flags = dhts_b200.Flags(dev)
-    full = _arz_pass(F, flags, r0, u0, gr, gu, w, T, 32)
+    full = _arz_pass(F, flags, r0, u0, gr, gu, w, T, 1)
     flags.check()
     assert all(torch.isfinite(x).all() for x in full)
     assert (full[2][1::2] == 0).all() and (full[3][1::2] == 0).all() and full[2][0::2].abs().max() > 0
     # shard == unshard, bitwise (three uneven shards)
     for lo, hi in ((0, 20000), (20000, 20001), (20001, B)):
-        part = _arz_pass(F, flags, r0[lo:hi], u0[lo:hi], gr[lo:hi], gu[lo:hi], w[lo:hi], T, 32)
+        part = _arz_pass(F, flags, r0[lo:hi], u0[lo:hi], gr[lo:hi], gu[lo:hi], w[lo:hi], T, 1)
         for a, b in zip(full, part):
             assert torch.equal(a[lo:hi], b)
     # lane permutation equivariance, bitwise
     perm = torch.randperm(B, generator=g, device=dev)
-    pp = _arz_pass(F, flags, r0[perm], u0[perm], gr[perm], gu[perm], w[perm], T, 32)
+    pp = _arz_pass(F, flags, r0[perm], u0[perm], gr[perm], gu[perm], w[perm], T, 1)
     for a, b in zip(full, pp):
         assert torch.equal(a[perm], b)
     del pp
     # checkpoint interval changes what is stored, not what is computed
-    for K in (7, 96, 200):
+    for K in (7, 32, 96, 200):
         kk = _arz_pass(F, flags, r0, u0, gr, gu, w, T, K)
         for a, b in zip(full, kk):
             assert torch.equal(a, b)
