@@ -38,8 +38,15 @@ def main():
     ap.add_argument("--precision", default="mixed", help="drop-in arithmetic: mixed (= the reference as shipped) / float64 / float32")
     ap.add_argument("--cpu-standin", action="store_true",
                     help="TEST ONLY: route the drop-in's kernel calls through tests/cpu_standin.py (host-logic check on a box without a GPU)")
+    ap.add_argument("--fp64", action="store_true",
+                    help="run everything in float64: the reference through the no-edit dtype rebinding of SURVEY App. C "
+                         "(its modules' np.float32 / th.float32 names point at the 64-bit types), the drop-in with "
+                         "precision=float64; the drivers' own tensors via problem.dtype and torch's default dtype")
+    ap.add_argument("--no-defer", action="store_true", help="drop-in: step every RoadNetwork.forward immediately")
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
+    if a.fp64:
+        a.precision = "float64"
 
     import numpy as np
     import torch as th
@@ -49,6 +56,8 @@ def main():
     if a.impl == "dropin":
         import dhts_b200.dropin as dropin
         dropin.install(precision=a.precision)
+        if a.no_defer:
+            dropin.runtime.configure(defer=False)
         install_ref.add_to_path(with_core=False)
         if a.cpu_standin:
             sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -57,6 +66,27 @@ def main():
             ctx.__enter__()
     else:
         install_ref.add_to_path(with_core=True)
+    if a.fp64:
+        th.set_default_dtype(th.float64)
+        if a.impl == "reference":
+            class _NP64:
+                float32 = np.float64
+
+                def __getattr__(self, k):
+                    return getattr(np, k)
+
+            class _TH64:
+                float32 = th.float64
+
+                def __getattr__(self, k):
+                    return getattr(th, k)
+
+            import model.macro.darz as m0, road.lane.dmacro_lane as m1, road.lane._macro_lane as m2
+            import road.lane.dmicro_lane as m3, road.lane._micro_lane as m4, model.micro.didm as m5
+            for m in (m0, m1, m2, m3):
+                m.np = _NP64()
+            for m in (m1, m2, m3, m4, m5):
+                m.th = _TH64()
     import road.lane.dmacro_lane as probe
     core = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(probe.__file__))))
 
@@ -75,6 +105,8 @@ def main():
         from example.inverse.hybrid import HybridInverseProblem
         problem = HybridInverseProblem(1, T, a.episodes, dt, umax, run_name, n, 5.0)
 
+    if a.fp64:
+        problem.dtype = th.float64
     # torch imports its compiler stack the first time an optimizer is built and stepped (seconds, once per
     # process): do that before the clock starts
     w = th.zeros(2, requires_grad=True)

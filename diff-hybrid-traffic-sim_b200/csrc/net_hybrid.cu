@@ -452,7 +452,8 @@ template <typename T> __device__ __forceinline__ HybSm<T> hyb_carve(const HybArg
 // headh [T][R][ML][2]: head deltas every micro lane used at step t.
 template <typename T>
 __global__ void __launch_bounds__(HYB_THREADS_MAX) hyb_rollout_fwd_kernel(HybArgs<T> a, const T* __restrict__ r0, const T* __restrict__ y0,
-                                                                          const T* __restrict__ u0, const T* __restrict__ own0,
+                                                                          const T* __restrict__ u0, const T* __restrict__ ueq0,
+                                                                          const T* __restrict__ own0,
                                                                           const T* __restrict__ aux0, T* __restrict__ hist,
                                                                           T* __restrict__ ownh, T* __restrict__ auxh,
                                                                           T* __restrict__ headh, int* __restrict__ flags) {
@@ -467,7 +468,9 @@ __global__ void __launch_bounds__(HYB_THREADS_MAX) hyb_rollout_fwd_kernel(HybArg
         for (int c = threadIdx.x; c < NC; c += blockDim.x) {
             const T r = r0[(size_t)b * NC + c];
             s.st[0][c] = r; s.st[0][NC + c] = y0[(size_t)b * NC + c]; s.st[0][2 * NC + c] = u0[(size_t)b * NC + c];
-            s.st[0][3 * NC + c] = u_eq(r, a.n.umax);                             // set_r_u, _arz.py:82-86
+            // stored u_eq: as set_r_u leaves it (_arz.py:82-86) unless the caller hands over what the cells hold
+            // (cleared cells carry u_max, cells rewritten by micro_to_macro a stale value: conversion.py:157-167)
+            s.st[0][3 * NC + c] = ueq0 ? ueq0[(size_t)b * NC + c] : u_eq(r, a.n.umax);
         }
         for (int c = threadIdx.x; c < 2 * n_own; c += blockDim.x) s.own[0][c] = own0[(size_t)b * 2 * n_own + c];
         for (int c = threadIdx.x; c < AUX; c += blockDim.x) s.aux[0][c] = aux0[(size_t)b * AUX + c];
@@ -900,9 +903,9 @@ static HybArgs<T> hyb_args(const dhts_hyb_topology* tp, const T* dx, const T* la
                                                const int* route, int route_per_replica, const int* spawn_route,        \
                                                int spawn_per_replica, int KS, const T* sig, const T* incoming,         \
                                                const T* veh_par, T umax, T dt, int steps, int R, int mode, int soft,   \
-                                               const T* r0, const T* y0, const T* u0, const T* own0, const T* aux0,    \
-                                               T* hist, T* own_hist, T* aux_hist, T* head_hist, int* flags,            \
-                                               void* stream) {                                                         \
+                                               const T* r0, const T* y0, const T* u0, const T* ueq0, const T* own0,    \
+                                               const T* aux0, T* hist, T* own_hist, T* aux_hist, T* head_hist,         \
+                                               int* flags, void* stream) {                                             \
         if (!topo || !veh_par || !r0 || !y0 || !u0 || !aux0 || !hist || !aux_hist || !flags) return DHTS_ERR_INVALID;  \
         dhts::HybArgs<T> a = dhts::hyb_args<T>(topo, dx, lane_len, route, route_per_replica, spawn_route,              \
                                                spawn_per_replica, KS, sig, incoming, veh_par, umax, dt, steps, R,      \
@@ -916,9 +919,9 @@ static HybArgs<T> hyb_args(const dhts_hyb_topology* tp, const T* dx, const T* la
         int grid = 1;                                                                                                  \
         rc = dhts::hyb_launch_cfg(dhts::hyb_rollout_fwd_kernel<T>, smem, threads, R, &grid);                           \
         if (rc) return rc;                                                                                             \
-        dhts::hyb_rollout_fwd_kernel<T><<<grid, threads, smem, (cudaStream_t)stream>>>(a, r0, y0, u0, own0, aux0,      \
-                                                                                         hist, own_hist, aux_hist,    \
-                                                                                         head_hist, flags);            \
+        dhts::hyb_rollout_fwd_kernel<T><<<grid, threads, smem, (cudaStream_t)stream>>>(a, r0, y0, u0, ueq0, own0,      \
+                                                                                         aux0, hist, own_hist,        \
+                                                                                         aux_hist, head_hist, flags);  \
         return cudaGetLastError() == cudaSuccess ? DHTS_OK : DHTS_ERR_CUDA;                                            \
     }                                                                                                                  \
     DHTS_EXPORT int dhts_hyb_rollout_bwd_##SUF(const dhts_hyb_topology* topo, const T* dx, const T* lane_len,          \

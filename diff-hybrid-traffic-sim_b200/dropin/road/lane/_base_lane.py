@@ -2,13 +2,33 @@
 from typing import Dict
 
 
+def synced(name):
+    """Attribute stored under `name` whose every read / write first executes the network's queued steps."""
+    def get(self):
+        self._sync()
+        return self.__dict__[name]
+
+    def put(self, value):
+        if "_net" in self.__dict__:
+            self._sync()
+        self.__dict__[name] = value
+    return property(get, put)
+
+
 class BaseLane:
     def __init__(self, id: int, length: float, speed_limit: float):
+        self._net = None        # the RoadNetwork this lane was added to: owner of the queue of deferred steps
         self.id = id
         self.length = length
         self.speed_limit = speed_limit
         self.next_lane: Dict[int, "BaseLane"] = {}
         self.prev_lane: Dict[int, "BaseLane"] = {}
+
+    def _sync(self):
+        """Run the steps the network has queued (dropin/deferred.py) before lane state is read or changed."""
+        net = self._net
+        if net is not None and net._pending:
+            net.flush()
 
     # kind / step hooks: filled in by MacroLane and MicroLane
     def is_macro(self):

@@ -20,7 +20,7 @@ import torch
 from dhts_b200 import functional as F
 from dhts_b200.dropin import runtime as rt
 from model.macro._arz import ARZ
-from road.lane._base_lane import BaseLane
+from road.lane._base_lane import BaseLane, synced
 
 _FIELDS = ("r", "y", "u", "e")
 
@@ -37,6 +37,11 @@ class MacroLane(BaseLane):
         def __init__(self, start, end, speed_limit):
             self.start, self.end = start, end
             self.state = ARZ.FullQ(speed_limit)
+
+    # state a queued network step would change: reads and writes run the queue first (dropin/deferred.py)
+    curr_cell = synced("_curr_cell")
+    next_cell = synced("_next_cell")
+    flux_capacitor = synced("_flux_capacitor")
 
     def __init__(self, id: int, lane_length: float, speed_limit: float, cell_length: float):
         super().__init__(id, lane_length, speed_limit)

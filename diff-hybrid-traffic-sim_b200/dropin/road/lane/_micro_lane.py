@@ -13,7 +13,7 @@ import torch
 from dhts_b200 import functional as F
 from dhts_b200.dropin import runtime as rt
 from dmath.operation import sigmoid
-from road.lane._base_lane import BaseLane
+from road.lane._base_lane import BaseLane, synced
 from road.vehicle.micro_vehicle import MicroVehicle
 
 DEFAULT_HEAD_POSITION_DELTA = 1000
@@ -22,6 +22,11 @@ POSITION_DELTA_EPS = 1e-5
 
 
 class MicroLane(BaseLane):
+    # state a queued network step would change: reads and writes run the queue first (dropin/deferred.py)
+    curr_vehicle = synced("_curr_vehicle")
+    next_vehicle_position = synced("_next_vehicle_position")
+    next_vehicle_speed = synced("_next_vehicle_speed")
+
     def __init__(self, id: int, lane_length: float, speed_limit: float):
         super().__init__(id, lane_length, speed_limit)
         self.curr_vehicle: List[MicroVehicle] = []

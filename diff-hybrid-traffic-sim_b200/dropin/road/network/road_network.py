@@ -11,6 +11,7 @@ from typing import Dict
 
 import numpy as np
 
+from dhts_b200.dropin import deferred
 from dhts_b200.dropin import runtime as rt
 from road.lane._base_lane import BaseLane
 from road.lane._macro_lane import MacroLane
@@ -22,8 +23,31 @@ from road.vehicle.micro_vehicle import DEFAULT_VEHICLE_LENGTH, MicroVehicle
 MAX_ROUTE_LENGTH = 32
 
 
+def _synced(name):
+    """Network attribute a queued step would change: reads and writes run the queue first (dropin/deferred.py)."""
+    def get(self):
+        if self.__dict__.get("_pending"):
+            self.flush()
+        return self.__dict__[name]
+
+    def put(self, value):
+        if self.__dict__.get("_pending"):
+            self.flush()
+        self.__dict__[name] = value
+    return property(get, put)
+
+
 class RoadNetwork:
+    vehicle = _synced("_vehicle")
+    micro_route = _synced("_micro_route")
+    macro_route = _synced("_macro_route")
+    num_vehicle = _synced("_num_vehicle")
+
     def __init__(self, speed_limit: float):
+        self._pending = 0                 # forward() calls queued for one fused rollout launch (dropin/deferred.py)
+        self._pending_dt = self._pending_diff = self._pending_mode = None
+        self._defer_cache = {}
+        self._stepped_once = False
         self.lane: Dict[int, BaseLane] = {}
         self.speed_limit = speed_limit                  # one limit for the whole network
         self.vehicle_length = DEFAULT_VEHICLE_LENGTH    # one vehicle length for the whole network
@@ -36,8 +60,10 @@ class RoadNetwork:
     # ------------------------------------------------------------------ construction
     def add_lane(self, lane: BaseLane):
         assert isinstance(lane, (MacroLane, MicroLane)), ""
+        self.flush()
         lane.speed_limit = self.speed_limit
         lane.id = self.num_lane
+        lane._net = self
         self.lane[lane.id] = lane
         self.num_lane += 1
         return lane.id
@@ -54,12 +80,34 @@ class RoadNetwork:
         return nv.id
 
     def connect_lane(self, prev_lane_id: int, next_lane_id: int):
+        self.flush()
         a, b = self.lane[prev_lane_id], self.lane[next_lane_id]
         a.add_next_lane(b)
         b.add_prev_lane(a)
 
     # ------------------------------------------------------------------ the step
     def forward(self, delta_time: float, differentiable: bool):
+        """One step of the whole network.  The step is QUEUED when the network is one the fused rollout kernels can take
+        (dropin/deferred.py) and runs, together with the steps queued after it, when its result is first looked at."""
+        mode = deferred.plan(self)
+        if mode is None or not self._stepped_once:
+            # also the very first step of a network runs at once: a time step that violates the CFL condition then raises
+            # here, inside forward(), as in the reference (_macro_lane.py:141-146); later ones raise at the flush
+            self.flush()
+            self._stepped_once = True
+            return self._forward_now(delta_time, differentiable)
+        if self._pending and (delta_time != self._pending_dt or differentiable != self._pending_diff
+                              or mode != self._pending_mode):
+            self.flush()
+        self._pending_dt, self._pending_diff, self._pending_mode = delta_time, differentiable, mode
+        self._pending += 1
+
+    def flush(self):
+        """Run the queued steps now."""
+        if self._pending:
+            deferred.flush(self)
+
+    def _forward_now(self, delta_time: float, differentiable: bool):
         lanes = list(self.lane.values())
         for lane in lanes:
             self.setup_boundary(lane.id, differentiable)

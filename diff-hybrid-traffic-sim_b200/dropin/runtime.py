@@ -14,17 +14,28 @@ import os
 import torch
 
 _PRECISIONS = ("mixed", "float64", "float32")
-_cfg = {"precision": os.environ.get("DHTS_PRECISION", "mixed"), "device": os.environ.get("DHTS_DEVICE")}
+_cfg = {"precision": os.environ.get("DHTS_PRECISION", "mixed"), "device": os.environ.get("DHTS_DEVICE"),
+        "defer": os.environ.get("DHTS_DEFER", "1") != "0", "defer_hyb": os.environ.get("DHTS_DEFER_HYB", "1") != "0"}
 _flags = {}
 
 
-def configure(precision=None, device=None):
+def configure(precision=None, device=None, defer=None, defer_hyb=None):
+    """defer: queue RoadNetwork.forward calls and run them as fused rollouts (dropin/deferred.py); defer_hyb: also for
+    connected macro / micro networks."""
+    if defer is not None:
+        _cfg["defer"] = bool(defer)
+    if defer_hyb is not None:
+        _cfg["defer_hyb"] = bool(defer_hyb)
     if precision is not None:
         if precision not in _PRECISIONS:
             raise ValueError("precision must be one of %s" % (_PRECISIONS,))
         _cfg["precision"] = precision
     if device is not None:
         _cfg["device"] = str(device)
+
+
+def defer_enabled(kind=None) -> bool:
+    return bool(_cfg["defer"] and (kind != "hyb" or _cfg["defer_hyb"]))
 
 
 def device() -> torch.device:

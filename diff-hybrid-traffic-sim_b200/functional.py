@@ -67,6 +67,18 @@ def arz_rollout(r0, u0, ghost_r, ghost_u, dx, umax, dt, steps, ckpt_every=32, fl
     return r, y, u
 
 
+def arz_rollout_state(r0, y0, u0, ghost, dx, umax, dt, steps, ckpt_every, flags):
+    """The rollout operator on lane STATE as the lanes hold it: (r0, y0)[B, N] differentiable, u0 the speed stored on
+    the cells (value only), ghost [B, 2, 3] = (r, y, u) per side, dx / umax [B].  Returns (rT, yT, uT).  What the
+    drop-in network's deferred stepping calls (dropin/deferred.py)."""
+    return ArzRolloutFn.apply(r0, y0, u0.detach(), ghost, dx, umax, dt, steps, ckpt_every, flags.t, None)
+
+
+def idm_rollout_state(p0, v0, params, lane_off, head, dt, steps, ckpt_every, flags, max_lane):
+    """The IDM rollout operator without the per-step fallback of `idm_rollout` (raises UnsupportedShape instead)."""
+    return IdmRolloutFn.apply(p0, v0, head, params, lane_off, max_lane, dt, steps, ckpt_every, flags.t)
+
+
 def arz_rollout_plan(B, N, steps, dtype, device, mem_fraction=0.6, min_lanes=296):
     """How to run a differentiable rollout of B lanes within the device's free memory: returns
     (lanes_per_chunk, ckpt_every).  Storing EVERY state (ckpt_every = 1) removes the segment recompute from

@@ -272,7 +272,7 @@ class HybRolloutFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, r0, y0, u0, own0, sig, incoming, aux0, topo: HybridNetTopology, route, spawn_route, veh_par, umax, dt,
-                steps, soft, flags):
+                steps, soft, flags, ueq0=None):
         dev = _lib.require_cuda(r0, y0, u0, own0, sig, incoming, aux0, route, spawn_route, flags)
         ctx.set_materialize_grads(False)      # an output nobody differentiates stays None in backward (no zero-filled history)
         c = lambda t: None if t is None else t.contiguous()
@@ -307,7 +307,7 @@ class HybRolloutFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             check(fn(topo.struct_ptr(), ptr(topo.real("dx", dtype)), ptr(topo.real("lane_len", dtype)), ptr(route), per_rep,
                      ptr(spawn_route), sp_rep, KS, ptr(sig), ptr(incoming), par, creal(dtype, umax), creal(dtype, dt), steps, R,
-                     topo.mode, int(bool(soft)), ptr(r0), ptr(y0), ptr(u0), ptr(own0 if topo.n_own else None), ptr(aux0),
+                     topo.mode, int(bool(soft)), ptr(r0), ptr(y0), ptr(u0), ptr(c(ueq0)), ptr(own0 if topo.n_own else None), ptr(aux0),
                      ptr(hist), ptr(ownh if topo.n_own else None), ptr(auxh), ptr(headh if topo.ML else None), ptr(flags),
                      stream_ptr(dev)), "dhts_hyb_rollout_fwd")
         ctx.save_for_backward(hist, ownh, auxh, sig, incoming, route, spawn_route)
@@ -345,7 +345,7 @@ class HybRolloutFn(torch.autograd.Function):
             g_aux0 = g_aux0 + g_auxh[0] * m
         need = ctx.needs_input_grad
         out = (g_r0, g_y0, g_u0, g_own0[:, :topo.n_own] if topo.n_own else None, g_sig, g_inc, g_aux0)
-        return tuple(g if need[i] else None for i, g in enumerate(out)) + (None,) * 9
+        return tuple(g if need[i] else None for i, g in enumerate(out)) + (None,) * 10
 
 
 class HybridStates:

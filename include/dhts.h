@@ -252,6 +252,8 @@ int dhts_c2m_bwd_f32(const float* p_head, const float* v_head, const float* a_he
  *                    side (differentiable=True), 0: sig > 0.5
  *   qk [steps] or NULL: sigmoid constant of the queue reward per step; reward [R] = -sum_t sum_lanes q^2 dt
  *   r0, y0, u0 [R][NC]; own0 [R][n_own][2] initial (r, u) of the own ghost records
+ *   ueq0 [R][NC] or NULL     u_eq STORED on the cells at the start (the step reads the stored value: cleared cells carry
+ *                            u_max, cells rewritten by micro_to_macro a stale one); NULL = u_eq(r0) as set_r_u leaves it
  *   hist [steps+1][R][3][NC]  every state (r, y, u): before step t, and after the last step (output, kept for bwd)
  *   own_hist [steps+1][R][n_own][2]
  * Backward:
@@ -349,8 +351,8 @@ int dhts_hyb_aux_size(const dhts_hyb_topology* topo);
 int dhts_hyb_rollout_fwd_f64(const dhts_hyb_topology* topo, const double* dx, const double* lane_len, const int* route,
                              int route_per_replica, const int* spawn_route, int spawn_per_replica, int KS,
                              const double* sig, const double* incoming, const double* veh_par, double umax, double dt, int steps,
-                             int R, int mode, int soft, const double* r0, const double* y0, const double* u0, const double* own0,
-                             const double* aux0, double* hist, double* own_hist, double* aux_hist, double* head_hist, int* flags,
+                             int R, int mode, int soft, const double* r0, const double* y0, const double* u0, const double* ueq0,
+                             const double* own0, const double* aux0, double* hist, double* own_hist, double* aux_hist, double* head_hist, int* flags,
                              void* stream);
 int dhts_hyb_rollout_bwd_f64(const dhts_hyb_topology* topo, const double* dx, const double* lane_len, const int* route,
                              int route_per_replica, const int* spawn_route, int spawn_per_replica, int KS,
@@ -361,8 +363,8 @@ int dhts_hyb_rollout_bwd_f64(const dhts_hyb_topology* topo, const double* dx, co
 int dhts_hyb_rollout_fwd_f32(const dhts_hyb_topology* topo, const float* dx, const float* lane_len, const int* route,
                              int route_per_replica, const int* spawn_route, int spawn_per_replica, int KS,
                              const float* sig, const float* incoming, const float* veh_par, float umax, float dt, int steps,
-                             int R, int mode, int soft, const float* r0, const float* y0, const float* u0, const float* own0,
-                             const float* aux0, float* hist, float* own_hist, float* aux_hist, float* head_hist, int* flags,
+                             int R, int mode, int soft, const float* r0, const float* y0, const float* u0, const float* ueq0,
+                             const float* own0, const float* aux0, float* hist, float* own_hist, float* aux_hist, float* head_hist, int* flags,
                              void* stream);
 int dhts_hyb_rollout_bwd_f32(const dhts_hyb_topology* topo, const float* dx, const float* lane_len, const int* route,
                              int route_per_replica, const int* spawn_route, int spawn_per_replica, int KS,

@@ -138,6 +138,23 @@ def micro_to_macro(p_head, v_head, a_head, len_head, lane_len, r, y, u, dx, umax
     return torch.stack(r_out), torch.stack(y_out), torch.stack(u_out), absorbed, ntouched
 
 
+def arz_rollout_state(r0, y0, u0, ghost, dx, umax, dt, steps, ckpt_every, flags):
+    """Stand-in of the fused ARZ rollout operator: the one-step stand-in chained `steps` times over static ghosts."""
+    r, y, u = r0, y0, u0.detach()
+    ue = None
+    for _ in range(int(steps)):
+        pad = lambda x, k: torch.cat([ghost[:, 0:1, k], x, ghost[:, 1:2, k]], dim=1)
+        r, y, u = arz_step(pad(r, 0), pad(y, 1), pad(u, 2).detach(), dx, umax, dt, flags)
+    return r, y, u
+
+
+def idm_rollout_state(p0, v0, params, lane_off, head, dt, steps, ckpt_every, flags, max_lane):
+    p, v = p0, v0
+    for _ in range(int(steps)):
+        p, v = idm_step(p, v, params, lane_off, head, dt, flags)
+    return p, v
+
+
 @contextlib.contextmanager
 def patched(precision="float64"):
     """Route the drop-in lanes through the stand-ins above, on the CPU.  Restores everything on exit."""
@@ -145,15 +162,20 @@ def patched(precision="float64"):
     from dhts_b200 import functional as F
     from dhts_b200.dropin import runtime as rt
     dropin.install(precision=precision)
-    saved = {k: getattr(F, k) for k in ("arz_step", "idm_step", "macro_to_micro", "micro_to_macro")}
+    saved = {k: getattr(F, k) for k in ("arz_step", "idm_step", "macro_to_micro", "micro_to_macro", "arz_rollout_state",
+                                        "idm_rollout_state")}
     saved_dev, saved_flags = rt.device, dict(rt._flags)
     F.arz_step, F.idm_step, F.macro_to_micro, F.micro_to_macro = arz_step, idm_step, macro_to_micro, micro_to_macro
+    F.arz_rollout_state, F.idm_rollout_state = arz_rollout_state, idm_rollout_state
     rt.device = lambda: torch.device("cpu")
     rt._flags.clear()
+    saved_hyb = rt._cfg["defer_hyb"]
+    rt.configure(defer_hyb=False)          # the fused hybrid rollout has no CPU stand-in: connected networks step immediately
     try:
         yield
     finally:
         for k, v in saved.items():
             setattr(F, k, v)
         rt.device = saved_dev
+        rt.configure(defer_hyb=saved_hyb)
         rt._flags.clear(); rt._flags.update(saved_flags)

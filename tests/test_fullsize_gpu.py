@@ -45,10 +45,16 @@ def test_arz_full_batch_invariances(dev):
     for a, b in zip(full, pp):
         assert torch.equal(a[perm], b)
     del pp
-    # checkpoint interval changes what is stored, not what is computed
-    for K in (7, 32, 96, 200):
+    # sparse checkpoints + segment recompute is a separate instantiation of the adjoint kernel (the compiler is free to
+    # contract its multiply-adds differently): same forward states bitwise, gradients to rounding
+    k32 = _arz_pass(F, flags, r0, u0, gr, gu, w, T, 32)
+    assert torch.equal(full[0], k32[0]) and torch.equal(full[1], k32[1])
+    for a, b in zip(full[2:], k32[2:]):
+        assert float((a - b).abs().max()) <= 1e-11 * float(a.abs().max())
+    # within that mode the checkpoint interval changes what is stored, not what is computed
+    for K in (7, 96, 200):
         kk = _arz_pass(F, flags, r0, u0, gr, gu, w, T, K)
-        for a, b in zip(full, kk):
+        for a, b in zip(k32, kk):
             assert torch.equal(a, b)
     flags.check()
 

@@ -56,8 +56,12 @@ def test_arz_headline_modes_vs_oracle(dev):
     assert abs(loss1 - ref_loss) <= 1e-9 * abs(ref_loss)
     del arena
     k32, loss32 = run(32, [(0, B)], None)
-    for name in k1:
-        assert torch.equal(k1[name], k32[name]), name       # the interval changes what is stored, not what is computed
+    for name, tol in (("rT", 1e-9), ("uT", 1e-9), ("g_r0", 1e-8), ("g_u0", 1e-8)):
+        assert relerr(k32[name].cpu(), o[name]) < tol, name
+    # same forward kernel -> identical states; the recompute adjoint is another instantiation -> gradients to rounding
+    assert torch.equal(k1["rT"], k32["rT"]) and torch.equal(k1["uT"], k32["uT"])
+    for name in ("g_r0", "g_u0"):
+        assert float((k1[name] - k32[name]).abs().max()) <= 1e-11 * float(k1[name].abs().max()), name
     assert loss32 == pytest.approx(loss1, rel=1e-12)
 
 
