@@ -640,14 +640,28 @@ static int sm_count_r() {
 // Measured on B200 (profiles/r1e sweep, fp64, 8192 lanes x 1024 cells): both kernels are fastest with 4 cells per
 // thread capped at 128 registers (2 CTAs of 256 threads per SM) -- forward 57 ms vs 69-89 ms for the other
 // shapes, adjoint 97 ms (every state stored) / 149 ms (K = 32) vs 106-226 ms.
+// Tuning knobs (environment), read ONCE per process: cells per thread, adjoint ring stages, forward staging.
+struct Knobs { int c_fwd, c_bwd, ring, stage; };
+static const Knobs& knobs() {
+    static const Knobs k = [] {
+        Knobs x{4, 4, 4, 1};
+        auto cells = [](const char* name, int dflt) {
+            const char* e = getenv(name);
+            if (!e) e = getenv("DHTS_ARZ_C");
+            if (!e) return dflt;
+            const int c = atoi(e);
+            return (c == 1 || c == 2 || c == 4 || c == 8) ? c : dflt;
+        };
+        x.c_fwd = cells("DHTS_ARZ_C_FWD", 4); x.c_bwd = cells("DHTS_ARZ_C_BWD", 4);
+        if (const char* e = getenv("DHTS_ARZ_RING")) x.ring = atoi(e);      // 0 = register prefetch
+        if (const char* e = getenv("DHTS_ARZ_STAGE")) x.stage = atoi(e);    // 0 = per-thread stores
+        return x;
+    }();
+    return k;
+}
+
 template <typename T> static int plan_reg(int B, int N, bool adj, RegPlan* p) {
-    int want = 4;
-    const char* e = getenv(adj ? "DHTS_ARZ_C_BWD" : "DHTS_ARZ_C_FWD");     // tuning knob: cells per thread
-    if (!e) e = getenv("DHTS_ARZ_C");
-    if (e) {
-        int c = atoi(e);
-        if (c == 1 || c == 2 || c == 4 || c == 8) want = c;
-    }
+    const int want = adj ? knobs().c_bwd : knobs().c_fwd;
     int C = 1;
     for (int c = 8; c > 1; c >>= 1)
         if (want >= c && N % c == 0 && N / c >= 32) { C = c; break; }
@@ -668,9 +682,7 @@ template <typename T> static int plan_reg(int B, int N, bool adj, RegPlan* p) {
         const size_t stage = (size_t)2 * lpc * N * sizeof(T);
         const size_t base = ring_offset<T>(lpc, p->threads / 32);
         const size_t budget = (C > 1 ? 112 : 224) * (size_t)1024;
-        int ns = 4;
-        const char* rg = getenv("DHTS_ARZ_RING");              // tuning knob: ring stages (0 = register prefetch)
-        if (rg) ns = atoi(rg);
+        int ns = knobs().ring;
         if (ns > 8) ns = 8;
         while (ns >= 2 && base + ns * (stage + 8) > budget) ns--;
         if (ns >= 2 && ((size_t)N * sizeof(T)) % 16 == 0 && (size_t)lpc * N * sizeof(T) < (1u << 19)) {
@@ -712,8 +724,7 @@ static int rollout_fwd(const T* r0, const T* y0, const T* u0, const T* ghost, co
     const size_t stage = (size_t)2 * p.lpc * N * sizeof(T);
     const size_t base = ring_offset<T>(p.lpc, p.threads / 32);
     bool staged = ckpt && K == 1 && p.C > 1 && ((size_t)N * sizeof(T)) % 16 == 0 && base + NSF * stage <= 112 * 1024;
-    const char* sg = getenv("DHTS_ARZ_STAGE");                 // tuning knob: 0 = per-thread stores
-    if (sg && atoi(sg) == 0) staged = false;
+    if (knobs().stage == 0) staged = false;
     if (staged) {
         const size_t smem = base + NSF * stage;
 #define CALL(CC, MB)                                                                                                   \

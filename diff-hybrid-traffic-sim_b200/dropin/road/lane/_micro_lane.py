@@ -96,13 +96,17 @@ class MicroLane(BaseLane):
         self._curr_views = (vp, vv)
 
     def _params(self, dtype):
+        """[6, n] IDM parameters of the vehicles on the lane.  The reference re-reads the six attributes of every
+        vehicle at every step (_micro_lane.py:195-214), so the cache is keyed on their VALUES (a tuple per vehicle),
+        not only on which vehicle objects are on the lane: an in-place edit of e.g. target_speed takes effect."""
         c = self._param_cache
         veh = self.curr_vehicle
-        if c is None or len(c[0]) != len(veh) or any(a is not b for a, b in zip(c[0], veh)) or c[1].dtype != dtype:
+        vals = [tuple(mv.idm_params()) for mv in veh]
+        if c is None or c[4] != vals or any(a is not b for a, b in zip(c[0], veh)) or c[1].dtype != dtype:
             n = len(veh)
-            par = torch.tensor([mv.idm_params() for mv in veh], dtype=dtype).t().contiguous().to(rt.device())
+            par = torch.tensor(vals, dtype=dtype).reshape(n, 6).t().contiguous().to(rt.device())
             off = torch.tensor([0, n], dtype=torch.int32, device=rt.device())
-            c = self._param_cache = (list(veh), par, off, torch.zeros(max(n, 1), dtype=torch.int32, device=rt.device()))
+            c = self._param_cache = (list(veh), par, off, torch.zeros(max(n, 1), dtype=torch.int32, device=rt.device()), vals)
         return c[1], c[2], c[3]
 
     def _head(self, dtype):

@@ -13,7 +13,7 @@ spawned into micro lane m; ``HybridNetTopology.random_spawn_routes`` draws them 
 every hop).  Only the part of a route up to its first macro lane matters (the vehicle is absorbed there), so routes
 are stored as "micro prefix + first macro lane".
 
-Restrictions (checked): every spawned vehicle has ``default_micro_vehicle`` parameters (one parameter set per
+Restrictions (checked): the micro lanes form no cycle (routes that revisit a lane are not enumerated); every spawned vehicle has ``default_micro_vehicle`` parameters (one parameter set per
 call); in ITSCP mode every micro lane has a predecessor (the stochastic waiting-list source of
 _simulator.py:153-174 is host-side and not fused).
 """
@@ -132,6 +132,26 @@ class HybridNetTopology:
         grp_off, grp_lane = [0], []
         for g in self.groups:
             grp_lane.extend(g); grp_off.append(len(grp_lane))
+        # The micro sub-graph must be ACYCLIC.  On a cycle the reference's create_random_route keeps its first choice once
+        # every successor is on the route already and lets the vehicle circulate for up to 32 hops (road_network.py:
+        # 628-640); those revisiting routes are not enumerated here (they grow combinatorially), so such networks are
+        # refused instead of being rolled out with vehicles that silently leave at the wrap-around.  The drop-in
+        # RoadNetwork steps them lane by lane.
+        state = {}
+
+        def cyclic(l):
+            if state.get(l) == 1:
+                return True
+            if state.get(l) == 2:
+                return False
+            state[l] = 1
+            hit = any(self.kind[x] and cyclic(x) for x in nxt[l])
+            state[l] = 2
+            return hit
+
+        if any(cyclic(l) for l in self.micro):
+            raise ValueError("HybridNetTopology: the micro lanes form a cycle; the fused hybrid rollout enumerates vehicle "
+                             "routes without revisits only (use the drop-in RoadNetwork for such networks)")
         # vehicle routes: micro prefix + first macro lane, enumerated from every micro lane
         self.routes: List[Tuple[int, ...]] = []
         self.route_index: Dict[Tuple[int, ...], int] = {}

@@ -81,6 +81,29 @@ class ArzStepFn(torch.autograd.Function):
         return g_r, g_y, None, None, None, None, None, None, None
 
 
+class _ArenaLease:
+    """Marks a caller-owned checkpoint arena as holding the states of a rollout whose backward has not run yet.
+    The kernels write the arena through raw pointers, so autograd's version counter cannot notice that a second
+    rollout overwrote it; this lease can: it lives in the first rollout's ctx, ends when its backward has read the
+    arena (or when the graph is dropped), and a rollout that finds a live lease on its arena raises."""
+    __slots__ = ("active", "__weakref__")
+
+    def __init__(self):
+        self.active = True
+
+
+def _lease_arena(buf):
+    import weakref
+    ref = getattr(buf, "_dhts_lease", None)
+    old = ref() if ref is not None else None
+    if old is not None and old.active:
+        raise RuntimeError("ckpt_buffer still holds the checkpoints of a rollout whose backward has not run: run that "
+                           "backward (or drop its graph) before reusing the arena, or pass another buffer")
+    lease = _ArenaLease()
+    buf._dhts_lease = weakref.ref(lease)
+    return lease
+
+
 class ArzRolloutFn(torch.autograd.Function):
     """(r0, y0)[B,N], ghost[B,2,3] -> (rT, yT, uT)[B,N] after `steps` fused steps with static ghosts."""
 
@@ -99,6 +122,7 @@ class ArzRolloutFn(torch.autograd.Function):
                 if ckpt_buffer.dtype != r0.dtype or ckpt_buffer.device != dev or ckpt_buffer.numel() < n:
                     raise ValueError("ckpt_buffer must be a %s tensor on %s with >= %d elements" % (r0.dtype, dev, n))
                 ckpt = ckpt_buffer.view(-1)[:n].view(S, 2, B, N)
+                ctx.lease = _lease_arena(ckpt_buffer)
             else:
                 ckpt = torch.empty((S, 2, B, N), dtype=r0.dtype, device=dev)
         rT = torch.empty_like(r0); yT = torch.empty_like(r0); uT = torch.empty_like(r0)
@@ -131,6 +155,9 @@ class ArzRolloutFn(torch.autograd.Function):
                                                 B, N, steps, K, ptr(rT), ptr(yT), ptr(g_rT), ptr(g_yT), ptr(g_uT),
                                                 ptr(scratch), ctypes.c_longlong(int(n)), ptr(g_r0), ptr(g_y0),
                                                 ptr(g_gh), ptr(flags), stream_ptr(dev)), "dhts_arz_rollout_bwd")
+        lease = getattr(ctx, "lease", None)
+        if lease is not None:
+            lease.active = False          # the arena has been read: the next rollout may overwrite it
         g_ghost = torch.zeros((B, 2, 3), dtype=dtype, device=dev)
         g_ghost[:, :, :2] = g_gh          # ghost u is a value-only input
         return g_r0, g_y0, None, g_ghost, None, None, None, None, None, None, None

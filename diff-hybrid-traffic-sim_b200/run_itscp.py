@@ -41,11 +41,25 @@ def main(argv=None):
     if ws > 1 and not torch.distributed.is_initialized():
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
         torch.distributed.init_process_group("nccl")
-    if args.seed > 0:
-        np.random.seed(args.seed); torch.manual_seed(args.seed)
+    rank = int(os.environ.get("RANK", "0"))
+    # Every rank must solve the SAME problem (inflow schedule, per-frame macro routes: both drawn from np.random in
+    # env.reset()) and write into the SAME result tree, or the all-reduced controller gradients / averaged evaluation
+    # rewards would mix different problems.  With --seed=0 (the reference default: unseeded) rank 0 draws a seed and a
+    # run name and broadcasts them.
+    seed, stamp = args.seed, int(time())
+    if ws > 1:
+        box = torch.tensor([seed if seed > 0 else int(np.random.randint(1, 2 ** 31 - 1)), stamp], dtype=torch.int64,
+                           device="cuda")
+        torch.distributed.broadcast(box, src=0)
+        seed, stamp = int(box[0]), int(box[1])
+    if seed > 0:
+        np.random.seed(seed); torch.manual_seed(seed)
     problem = {1: problem_1, 2: problem_2, 3: problem_3}[args.problem]
-    run_name = args.out or "./result/control/itscp/{}_{}".format(args.mode, int(time()))
-    os.makedirs(run_name, exist_ok=True)
+    run_name = args.out or "./result/control/itscp/{}_{}".format(args.mode, stamp)
+    if rank == 0:
+        os.makedirs(run_name, exist_ok=True)
+    if ws > 1:
+        torch.distributed.barrier()
 
     env = ItscpEnv()
     env.schedule_callback = problem
@@ -57,7 +71,7 @@ def main(argv=None):
     env.config["signal_length"] = args.signal_length
     env.config["mode"] = args.mode
     env.config["speed_limit"] = args.speed_limit
-    env.config["random_seed"] = args.seed
+    env.config["random_seed"] = seed          # > 0 under torchrun: env.reset() re-seeds np.random identically on every rank
     env.reset()
     curves = []
     for it in range(args.n_trial):

@@ -95,13 +95,19 @@ int dhts_arz_step_bwd_f32(const float* r_pad, const float* y_pad, const float* u
 /* ---------------------------------------------------------------- ARZ, fused T-step rollout
  * `steps` x (RoadNetwork.forward over disconnected macro lanes): ghosts are
  * static per lane (road/network/road_network.py:299-387 with no neighbour),
- * lane.forward, update_state.  The whole lane stays in shared memory.
+ * lane.forward, update_state.  A lane stays in the REGISTERS of the threads that
+ * own it for the whole rollout (1, 2, 4 or 8 consecutive cells per thread).
  *   r0, y0 [B][N]; u0 [B][N] or NULL (stored speed of the initial cells, set_r_u)
  *   ghost [B][2][3]        (r, y, u) of the left / right ghost cell
  *   ckpt [S][2][B][N] or NULL, S = ceil(steps/ckpt_every): state BEFORE steps
  *                          0, K, 2K, ... (needed by the backward entry point)
  *   rT, yT, uT [B][N]      final state, uT = compute_u(rT, yT)
- * Returns DHTS_ERR_UNSUPPORTED when a lane does not fit in shared memory.
+ * Limits of the fused kernels: a lane must fit one CTA -- N <= 1024 cells in general (one or two cells per thread),
+ * N <= 2048 when N is a multiple of 8 (256 threads x 8 cells; plan_reg in csrc/arz_rollout.cu) -- and with more than
+ * one cell per thread every array must be 16-byte aligned.  Otherwise the call returns DHTS_ERR_UNSUPPORTED and enqueues nothing; the host then chains
+ * `steps` launches of the one-step entry points (dhts_b200.functional.arz_rollout does).  The IDM rollouts take lanes
+ * of at most dhts_idm_rollout_max_lane() = 256 vehicles and checkpoint intervals up to
+ * dhts_idm_rollout_max_ckpt_every() = 32, with the same fallback.
  */
 int dhts_arz_rollout_fwd_f64(const double* r0, const double* y0, const double* u0, const double* ghost,
                              const double* dx, const double* umax, double dt, int B, int N, int steps, int ckpt_every,

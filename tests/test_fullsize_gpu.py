@@ -1,9 +1,9 @@
 """Size-independent properties at BASELINE.json's full per-GPU shapes (65536 lanes x 1024 cells; 4,194,304 vehicles
 in 65536 lanes), where the oracle cannot follow: lanes are independent, so results must be BITWISE invariant under
 sharding, lane permutation and the checkpoint interval, and a lane with zero loss weight must get an exactly zero
-gradient.  (Steps are kept at 96 so the test stays in seconds; the time loop is the same code for any T.)
+gradient.  (Steps are kept at 64 / 96 so the test stays in seconds; the time loop is the same code for any T.)
 The base run uses ckpt_every = 1 -- every state stored, TMA staging ring forward, TMA ring adjoint: the mode
-bench.py times (103 GB of stored states for the 65536 lanes x 96 steps here); the oracle comparison of that mode at
+bench.py times (69 GB of stored states for the 65536 lanes x 64 steps here); the oracle comparison of that mode at
 the full T = 1000 is tests/test_headline_gpu.py."""
 import pytest
 import torch
@@ -23,7 +23,7 @@ def _arz_pass(F, flags, r0, u0, gr, gu, w, T, K):
 def test_arz_full_batch_invariances(dev):
     import dhts_b200
     from dhts_b200 import functional as F
-    B, N, T = 65536, 1024, 96
+    B, N, T = 65536, 1024, 64
     g = torch.Generator(device=dev).manual_seed(SEED)
     rnd = lambda *s: torch.rand(s, generator=g, dtype=torch.float64, device=dev)
     r0, u0, gr, gu = rnd(B, N), rnd(B, N) * 30, rnd(B, 2), rnd(B, 2) * 30
@@ -36,15 +36,18 @@ def test_arz_full_batch_invariances(dev):
     assert (full[2][1::2] == 0).all() and (full[3][1::2] == 0).all() and full[2][0::2].abs().max() > 0
     # shard == unshard, bitwise (three uneven shards)
     for lo, hi in ((0, 20000), (20000, 20001), (20001, B)):
+        torch.cuda.empty_cache()          # the 69 GB state arena of the previous pass goes back to the driver (no fragmentation)
         part = _arz_pass(F, flags, r0[lo:hi], u0[lo:hi], gr[lo:hi], gu[lo:hi], w[lo:hi], T, 1)
         for a, b in zip(full, part):
             assert torch.equal(a[lo:hi], b)
     # lane permutation equivariance, bitwise
     perm = torch.randperm(B, generator=g, device=dev)
+    torch.cuda.empty_cache()
     pp = _arz_pass(F, flags, r0[perm], u0[perm], gr[perm], gu[perm], w[perm], T, 1)
     for a, b in zip(full, pp):
         assert torch.equal(a[perm], b)
     del pp
+    torch.cuda.empty_cache()
     # sparse checkpoints + segment recompute is a separate instantiation of the adjoint kernel (the compiler is free to
     # contract its multiply-adds differently): same forward states bitwise, gradients to rounding
     k32 = _arz_pass(F, flags, r0, u0, gr, gu, w, T, 32)
@@ -52,7 +55,7 @@ def test_arz_full_batch_invariances(dev):
     for a, b in zip(full[2:], k32[2:]):
         assert float((a - b).abs().max()) <= 1e-11 * float(a.abs().max())
     # within that mode the checkpoint interval changes what is stored, not what is computed
-    for K in (7, 96, 200):
+    for K in (7, 64, 200):
         kk = _arz_pass(F, flags, r0, u0, gr, gu, w, T, K)
         for a, b in zip(k32, kk):
             assert torch.equal(a, b)
