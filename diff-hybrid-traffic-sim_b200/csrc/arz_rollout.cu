@@ -641,10 +641,10 @@ static int sm_count_r() {
 // thread capped at 128 registers (2 CTAs of 256 threads per SM) -- forward 57 ms vs 69-89 ms for the other
 // shapes, adjoint 97 ms (every state stored) / 149 ms (K = 32) vs 106-226 ms.
 // Tuning knobs (environment), read ONCE per process: cells per thread, adjoint ring stages, forward staging.
-struct Knobs { int c_fwd, c_bwd, ring, stage; };
+struct Knobs { int c_fwd, c_bwd, ring, stage, mb_fwd; };
 static const Knobs& knobs() {
     static const Knobs k = [] {
-        Knobs x{4, 4, 4, 1};
+        Knobs x{4, 4, 4, 1, 3};
         auto cells = [](const char* name, int dflt) {
             const char* e = getenv(name);
             if (!e) e = getenv("DHTS_ARZ_C");
@@ -655,6 +655,7 @@ static const Knobs& knobs() {
         x.c_fwd = cells("DHTS_ARZ_C_FWD", 4); x.c_bwd = cells("DHTS_ARZ_C_BWD", 4);
         if (const char* e = getenv("DHTS_ARZ_RING")) x.ring = atoi(e);      // 0 = register prefetch
         if (const char* e = getenv("DHTS_ARZ_STAGE")) x.stage = atoi(e);    // 0 = per-thread stores
+        if (const char* e = getenv("DHTS_ARZ_MB_FWD")) x.mb_fwd = atoi(e);  // 3 (default) = 80-register forward kernel, 3 CTAs per SM: 384 vs 393 ms per pass (r2c A/B); 2 = 128 registers
         return x;
     }();
     return k;
@@ -736,7 +737,7 @@ static int rollout_fwd(const T* r0, const T* y0, const T* u0, const T* ghost, co
                                                                                   N, steps, K, p.lpc, ckpt, rT, yT,    \
                                                                                   uT, flags);                          \
     }
-        DHTS_C_DISPATCH(p, CALL)
+        if (p.C == 4 && knobs().mb_fwd == 3 && base + NSF * stage <= 74 * 1024) { CALL(4, 3) } else { DHTS_C_DISPATCH(p, CALL) }
 #undef CALL
     } else {
 #define CALL(CC, MB) arz_rollout_fwd_reg_kernel<T, CC, MB, 0><<<grid, p.threads, p.smem, st>>>(r0, y0, u0, ghost, dx, umax, dt, B, N, steps, K, p.lpc, ckpt, rT, yT, uT, flags);

@@ -13,7 +13,8 @@ spawned into micro lane m; ``HybridNetTopology.random_spawn_routes`` draws them 
 every hop).  Only the part of a route up to its first macro lane matters (the vehicle is absorbed there), so routes
 are stored as "micro prefix + first macro lane".
 
-Restrictions (checked): the micro lanes form no cycle (routes that revisit a lane are not enumerated); every spawned vehicle has ``default_micro_vehicle`` parameters (one parameter set per
+Restrictions: on a cycle of micro lanes a vehicle route ends where every successor has been visited (``cyclic_micro``;
+the reference would let it circulate for up to 32 hops); checked: every spawned vehicle has ``default_micro_vehicle`` parameters (one parameter set per
 call); in ITSCP mode every micro lane has a predecessor (the stochastic waiting-list source of
 _simulator.py:153-174 is host-side and not fused).
 """
@@ -132,11 +133,12 @@ class HybridNetTopology:
         grp_off, grp_lane = [0], []
         for g in self.groups:
             grp_lane.extend(g); grp_off.append(len(grp_lane))
-        # The micro sub-graph must be ACYCLIC.  On a cycle the reference's create_random_route keeps its first choice once
-        # every successor is on the route already and lets the vehicle circulate for up to 32 hops (road_network.py:
-        # 628-640); those revisiting routes are not enumerated here (they grow combinatorially), so such networks are
-        # refused instead of being rolled out with vehicles that silently leave at the wrap-around.  The drop-in
-        # RoadNetwork steps them lane by lane.
+        # Cycles in the micro sub-graph (e.g. the four centre intersections of a 4 x 4 ITSCP grid): once every successor
+        # is on the route already, the reference's create_random_route keeps its first choice and lets the vehicle
+        # circulate for up to 32 hops (road_network.py:628-640).  Those revisiting routes grow combinatorially and are
+        # NOT enumerated here: a route ends where every successor has been visited, and the vehicle leaves there through
+        # micro_to_none.  `cyclic_micro` records that this network is affected (the drop-in RoadNetwork, which draws
+        # routes exactly like the reference, is the path to use when circulating vehicles matter).
         state = {}
 
         def cyclic(l):
@@ -149,9 +151,7 @@ class HybridNetTopology:
             state[l] = 2
             return hit
 
-        if any(cyclic(l) for l in self.micro):
-            raise ValueError("HybridNetTopology: the micro lanes form a cycle; the fused hybrid rollout enumerates vehicle "
-                             "routes without revisits only (use the drop-in RoadNetwork for such networks)")
+        self.cyclic_micro = any(cyclic(l) for l in self.micro)
         # vehicle routes: micro prefix + first macro lane, enumerated from every micro lane
         self.routes: List[Tuple[int, ...]] = []
         self.route_index: Dict[Tuple[int, ...], int] = {}
