@@ -178,13 +178,13 @@ template <typename T, int C> __device__ __forceinline__ void store_chunk(T* __re
 constexpr int GH_F = RF_FWD, GH_A = 10;
 template <typename T> struct Shm {
     LaneK<T>* lk;     // [lpc]
-    T* ghostF;        // [lpc][2][GH_F]   left / right ghost forward records
-    T* ghostA;        // [lpc][2][GH_A]   left / right ghost adjoint records
+    T* ghostF;        // [2][lpc][2][GH_F]   left / right ghost forward records (second copy: per-step ghosts, by step parity)
+    T* ghostA;        // [2][lpc][2][GH_A]   left / right ghost adjoint records
     T* boxL;          // [2][nwarp][RF_ADJ]
     T* boxR;          // [2][nwarp][4]
 };
 template <typename T> __host__ __device__ inline size_t shm_bytes(int lpc, int nwarp) {
-    return sizeof(LaneK<T>) * lpc + sizeof(T) * ((size_t)lpc * 2 * (GH_F + GH_A) + (size_t)2 * nwarp * (RF_ADJ + 4)) + 16;
+    return sizeof(LaneK<T>) * lpc + sizeof(T) * ((size_t)lpc * 4 * (GH_F + GH_A) + (size_t)2 * nwarp * (RF_ADJ + 4)) + 16;
 }
 template <typename T> __host__ __device__ inline size_t ring_offset(int lpc, int nwarp) {
     return (shm_bytes<T>(lpc, nwarp) + 127) / 128 * 128;
@@ -193,7 +193,7 @@ template <typename T> __device__ __forceinline__ Shm<T> carve_shm(unsigned char*
     Shm<T> s;
     s.lk = reinterpret_cast<LaneK<T>*>(raw);
     T* p = reinterpret_cast<T*>(raw + sizeof(LaneK<T>) * lpc);
-    s.ghostF = p; p += lpc * 2 * GH_F; s.ghostA = p; p += lpc * 2 * GH_A;
+    s.ghostF = p; p += lpc * 4 * GH_F; s.ghostA = p; p += lpc * 4 * GH_A;
     s.boxL = p; p += 2 * nwarp * RF_ADJ; s.boxR = p;
     return s;
 }
@@ -202,7 +202,7 @@ template <typename T>
 __device__ __forceinline__ void setup_group(const Shm<T>& s, int lane0, int nl, const T* __restrict__ ghost,
                                             const T* __restrict__ dx, const T* __restrict__ umax_, T dt) {
     for (int l = threadIdx.x; l < nl; l += blockDim.x) s.lk[l] = make_lanek<T>(umax_[lane0 + l], dx[lane0 + l], dt);
-    for (int e = threadIdx.x; e < nl * 2; e += blockDim.x) {
+    for (int e = threadIdx.x; e < nl * 2 && ghost; e += blockDim.x) {      // ghost == null: per-step ghosts (step_ghost_record)
         int l = e >> 1, side = e & 1;
         const T* g = ghost + ((size_t)(lane0 + l) * 2 + side) * 3;          // (r, y, u) built by from_r_u
         const LaneK<T> k = make_lanek<T>(umax_[lane0 + l], dx[lane0 + l], dt);
@@ -214,6 +214,25 @@ __device__ __forceinline__ void setup_group(const Shm<T>& s, int lane0, int nl, 
         T tmp[RF_ADJ];
         pack(a, T(0), T(0), tmp);
         for (int i = 0; i < GH_A; i++) s.ghostA[(l * 2 + side) * GH_A + i] = tmp[i];
+    }
+}
+
+// Per-step ghosts (a lane inside a network gets new ghost cells every step, road_network.py:364-387): thread e < 2 nl
+// turns the (r, y, u) it prefetched for side e & 1 of lane e >> 1 into that step's records.
+template <typename T, bool ADJ>
+__device__ __forceinline__ void step_ghost_record(const Shm<T>& s, int e, int lpc, int par, const T* g) {
+    const LaneK<T> k = s.lk[e >> 1];
+    if (!ADJ) {
+        FRec<T> f = fderive<T, true>(g[0], g[1], g[2], k);
+        if (g[0] < DHTS_EPS) f.w = w_vacuum(g[0], f.us, k);
+        pack(f, s.ghostF + ((size_t)par * lpc * 2 + e) * GH_F);
+    } else {
+        ARec<T> a = aderive<T, true>(g[0], g[1], g[2], k);
+        if (g[0] < DHTS_EPS) fix_vacuum_adj(a, g[1], k);
+        T tmp[RF_ADJ];
+        pack(a, T(0), T(0), tmp);
+#pragma unroll
+        for (int i = 0; i < GH_A; i++) s.ghostA[((size_t)par * lpc * 2 + e) * GH_A + i] = tmp[i];
     }
 }
 
@@ -293,9 +312,10 @@ __device__ __forceinline__ bool chunk_fwd_step(T* r, T* y, const T* us, bool fir
 // NS > 0 (every state stored, K == 1): the state rows go to HBM through an NS-stage shared-memory staging ring and
 // TMA bulk stores issued by one thread -- no per-thread STG, no store address arithmetic, and the state registers
 // are free again as soon as the STS has read them.  NS == 0: per-thread vector stores (sparse checkpoints).
-template <typename T, int C, int MB, int NS>
+template <typename T, int C, int MB, int NS, bool TV = false>
 __global__ void __launch_bounds__(1024 / (C < 4 ? C : 4), MB) arz_rollout_fwd_reg_kernel(const T* __restrict__ r0, const T* __restrict__ y0,
                                            const T* __restrict__ u0, const T* __restrict__ ghost,
+                                           const T* __restrict__ ghost_t,
                                            const T* __restrict__ dx, const T* __restrict__ umax_, T dt, int B, int N,
                                            int steps, int K, int lpc, T* __restrict__ ckpt, T* __restrict__ rT,
                                            T* __restrict__ yT, T* __restrict__ uT, int* __restrict__ flags) {
@@ -323,6 +343,10 @@ __global__ void __launch_bounds__(1024 / (C < 4 ? C : 4), MB) arz_rollout_fwd_re
         const size_t soff = (size_t)ll * N + (size_t)kc * C;
         const bool first_chunk = kc == 0, last_chunk = kc == tpl - 1;
         const size_t BN = (size_t)B * N;
+        T gq[3] = {T(0), T(0), T(0)};                           // TV: ghost (r, y, u) of the coming step, thread e < 2 nl
+        const bool gthread = TV && (int)threadIdx.x < 2 * nl;
+        const T* gsrc = TV ? ghost_t + ((size_t)(lane0 + (threadIdx.x >> 1)) * 2 + (threadIdx.x & 1)) * 3 : nullptr;
+        if (gthread && steps > 0) { gq[0] = gsrc[0]; gq[1] = gsrc[1]; gq[2] = gsrc[2]; }
         T r[C], y[C];
         load_chunk<T, C>(r0 + off, r); load_chunk<T, C>(y0 + off, y);
         bool lbad = false;
@@ -333,6 +357,13 @@ __global__ void __launch_bounds__(1024 / (C < 4 ? C : 4), MB) arz_rollout_fwd_re
         const unsigned rowbytes = (unsigned)((size_t)nl * N * sizeof(T));
         int next_ck = 0;
         for (int t = 0; t < steps; t++) {
+            if (TV) {       // this step's ghost records (published by the step's first block barrier), then prefetch the next ones
+                if (gthread) {
+                    step_ghost_record<T, false>(s, threadIdx.x, lpc, t & 1, gq);
+                    if (t + 1 < steps) { const T* q = gsrc + (size_t)(t + 1) * B * 6; gq[0] = q[0]; gq[1] = q[1]; gq[2] = q[2]; }
+                }
+                gL = s.ghostF + ((size_t)(t & 1) * lpc * 2 + ll * 2) * GH_F; gR = gL + GH_F;
+            }
             const bool store_now = ck && t == next_ck;
             if (store_now) {
                 if (NS > 0) {
@@ -449,9 +480,13 @@ __device__ __forceinline__ bool chunk_adj_step(const T* r, const T* y, const T* 
 // MODE 0: every state stored, streamed back through the TMA ring;  1: every state stored, register prefetch;
 // 2: checkpoint every K steps, segment recompute with an L2-resident stash.  (Separate instantiations so that
 // each gets its own register allocation.)
-template <typename T, int C, int MB, int MODE>
+// EXT (MODE 1 only): per-step ghosts ghost_t [steps][B][2][3] with their adjoints g_ghost_t [steps][B][2][2], and g_hist
+// [steps][2][B][N], the adjoint of a loss that reads the state BEFORE every step (added once that step's VJP has run).
+template <typename T, int C, int MB, int MODE, bool EXT = false>
 __global__ void __launch_bounds__(1024 / (C < 4 ? C : 4), MB) arz_rollout_bwd_reg_kernel(const T* __restrict__ ckpt, const T* __restrict__ u0,
-                                           const T* __restrict__ ghost, const T* __restrict__ dx,
+                                           const T* __restrict__ ghost, const T* __restrict__ ghost_t,
+                                           const T* __restrict__ g_hist, T* __restrict__ g_ghost_t,
+                                           const T* __restrict__ dx,
                                            const T* __restrict__ umax_, T dt, int B, int N, int steps, int K, int lpc,
                                            const T* __restrict__ rT, const T* __restrict__ yT,
                                            const T* __restrict__ g_rT, const T* __restrict__ g_yT,
@@ -555,16 +590,44 @@ __global__ void __launch_bounds__(1024 / (C < 4 ? C : 4), MB) arz_rollout_bwd_re
             T r[C], y[C], rn[C], yn[C];
             const T* cr = ckpt + (size_t)(steps > 0 ? steps - 1 : 0) * 2 * BN + off;
             if (steps > 0) { load_chunk<T, C>(cr, r); load_chunk<T, C>(cr + BN, y); }
+            T gq[3] = {T(0), T(0), T(0)};
+            const bool tv = EXT && ghost_t != nullptr;
+            const bool gthread = tv && (int)threadIdx.x < 2 * nl;
+            const T* gsrc = tv ? ghost_t + ((size_t)(lane0 + (threadIdx.x >> 1)) * 2 + (threadIdx.x & 1)) * 3 : nullptr;
+            if (gthread && steps > 0) { const T* q = gsrc + (size_t)(steps - 1) * B * 6; gq[0] = q[0]; gq[1] = q[1]; gq[2] = q[2]; }
+            const T* gA_L = gLa; const T* gA_R = gRa;
             for (int t = steps - 1; t >= 0; t--) {
+                T hr[C], hy[C];
+                if (EXT && g_hist) {      // consumed at the end of the step: the loads fly during the step's arithmetic
+                    const T* q = g_hist + (size_t)t * 2 * BN + off;
+                    load_chunk<T, C>(q, hr); load_chunk<T, C>(q + BN, hy);
+                }
+                if (tv) {
+                    if (gthread) {
+                        step_ghost_record<T, true>(s, threadIdx.x, lpc, t & 1, gq);
+                        if (t > 0) { const T* q = gsrc + (size_t)(t - 1) * B * 6; gq[0] = q[0]; gq[1] = q[1]; gq[2] = q[2]; }
+                    }
+                    gA_L = s.ghostA + ((size_t)(t & 1) * lpc * 2 + ll * 2) * GH_A; gA_R = gA_L + GH_A;
+                }
                 if (t > 0) {
                     cr -= 2 * BN;
                     load_chunk<T, C>(cr, rn); load_chunk<T, C>(cr + BN, yn);
                 }
                 if (t == 0 && u0)
-                    { T us_[C]; load_chunk<T, C>(u0 + off, us_); nan |= chunk_adj_step<T, C, true>(r, y, us_, gr, gy, first_chunk, last_chunk, k, gLa, gRa, accL, accR, blA, brA, warp, nwarp, lane); }
+                    { T us_[C]; load_chunk<T, C>(u0 + off, us_); nan |= chunk_adj_step<T, C, true>(r, y, us_, gr, gy, first_chunk, last_chunk, k, gA_L, gA_R, accL, accR, blA, brA, warp, nwarp, lane); }
                 else
-                    nan |= chunk_adj_step<T, C, false>(r, y, nullptr, gr, gy, first_chunk, last_chunk, k, gLa, gRa, accL, accR, blA, brA, warp, nwarp, lane);
+                    nan |= chunk_adj_step<T, C, false>(r, y, nullptr, gr, gy, first_chunk, last_chunk, k, gA_L, gA_R, accL, accR, blA, brA, warp, nwarp, lane);
                 DHTS_SWAP_BOXES
+                if (tv && g_ghost_t && active) {      // this step's ghost adjoints leave; the accumulators restart
+                    T* gg = g_ghost_t + ((size_t)t * B + lane0 + ll) * 4;
+                    if (first_chunk) { gg[0] = accL[0]; gg[1] = accL[1]; bad |= t_isnan(accL[0]) || t_isnan(accL[1]); }
+                    if (last_chunk) { gg[2] = accR[0]; gg[3] = accR[1]; bad |= t_isnan(accR[0]) || t_isnan(accR[1]); }
+                }
+                if (tv) { accL[0] = accL[1] = accR[0] = accR[1] = T(0); }
+                if (EXT && g_hist) {
+#pragma unroll
+                    for (int c = 0; c < C; c++) { gr[c] += hr[c]; gy[c] += hy[c]; }
+                }
 #pragma unroll
                 for (int c = 0; c < C; c++) { r[c] = rn[c]; y[c] = yn[c]; }
             }
@@ -609,7 +672,7 @@ __global__ void __launch_bounds__(1024 / (C < 4 ? C : 4), MB) arz_rollout_bwd_re
         bad |= nan && active;
         if (active) {
             store_chunk<T, C>(g_r0 + off, gr); store_chunk<T, C>(g_y0 + off, gy);
-            if (g_ghost) {
+            if (g_ghost && !(EXT && ghost_t)) {
                 T* gg = g_ghost + (size_t)(lane0 + ll) * 4;
                 if (first_chunk) { gg[0] = accL[0]; gg[1] = accL[1]; bad |= t_isnan(accL[0]) || t_isnan(accL[1]); }
                 if (last_chunk) { gg[2] = accR[0]; gg[3] = accR[1]; bad |= t_isnan(accR[0]) || t_isnan(accR[1]); }
@@ -707,9 +770,9 @@ template <typename T> static int plan_reg(int B, int N, bool adj, RegPlan* p) {
 static int status_r() { return cudaGetLastError() == cudaSuccess ? DHTS_OK : DHTS_ERR_CUDA; }
 
 template <typename T>
-static int rollout_fwd(const T* r0, const T* y0, const T* u0, const T* ghost, const T* dx, const T* umax, T dt, int B,
-                       int N, int steps, int K, T* ckpt, T* rT, T* yT, T* uT, int* flags, cudaStream_t st) {
-    if (!r0 || !y0 || !ghost || !dx || !umax || !rT || !yT || !uT || !flags || B < 0 || N < 1 || steps < 0)
+static int rollout_fwd(const T* r0, const T* y0, const T* u0, const T* ghost, const T* ghost_t, const T* dx, const T* umax,
+                       T dt, int B, int N, int steps, int K, T* ckpt, T* rT, T* yT, T* uT, int* flags, cudaStream_t st) {
+    if (!r0 || !y0 || (!ghost && !ghost_t) || !dx || !umax || !rT || !yT || !uT || !flags || B < 0 || N < 1 || steps < 0)
         return DHTS_ERR_INVALID;
     if (ckpt && K < 1) return DHTS_ERR_INVALID;
     if (B == 0) return DHTS_OK;
@@ -726,21 +789,25 @@ static int rollout_fwd(const T* r0, const T* y0, const T* u0, const T* ghost, co
     const size_t base = ring_offset<T>(p.lpc, p.threads / 32);
     bool staged = ckpt && K == 1 && p.C > 1 && ((size_t)N * sizeof(T)) % 16 == 0 && base + NSF * stage <= 112 * 1024;
     if (knobs().stage == 0) staged = false;
-    if (staged) {
+    if (ghost_t) {      // per-step ghosts: the variant with per-thread checkpoint stores
+#define CALL(CC, MB) arz_rollout_fwd_reg_kernel<T, CC, MB, 0, true><<<grid, p.threads, p.smem, st>>>(r0, y0, u0, nullptr, ghost_t, dx, umax, dt, B, N, steps, K, p.lpc, ckpt, rT, yT, uT, flags);
+        DHTS_C_DISPATCH(p, CALL)
+#undef CALL
+    } else if (staged) {
         const size_t smem = base + NSF * stage;
 #define CALL(CC, MB)                                                                                                   \
     {                                                                                                                  \
         if (smem > 48 * 1024)                                                                                          \
             cudaFuncSetAttribute(arz_rollout_fwd_reg_kernel<T, CC, MB, NSF>,                                           \
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                              \
-        arz_rollout_fwd_reg_kernel<T, CC, MB, NSF><<<grid, p.threads, smem, st>>>(r0, y0, u0, ghost, dx, umax, dt, B,  \
+        arz_rollout_fwd_reg_kernel<T, CC, MB, NSF><<<grid, p.threads, smem, st>>>(r0, y0, u0, ghost, nullptr, dx, umax, dt, B,  \
                                                                                   N, steps, K, p.lpc, ckpt, rT, yT,    \
                                                                                   uT, flags);                          \
     }
         if (p.C == 4 && knobs().mb_fwd == 3 && base + NSF * stage <= 74 * 1024) { CALL(4, 3) } else { DHTS_C_DISPATCH(p, CALL) }
 #undef CALL
     } else {
-#define CALL(CC, MB) arz_rollout_fwd_reg_kernel<T, CC, MB, 0><<<grid, p.threads, p.smem, st>>>(r0, y0, u0, ghost, dx, umax, dt, B, N, steps, K, p.lpc, ckpt, rT, yT, uT, flags);
+#define CALL(CC, MB) arz_rollout_fwd_reg_kernel<T, CC, MB, 0><<<grid, p.threads, p.smem, st>>>(r0, y0, u0, ghost, nullptr, dx, umax, dt, B, N, steps, K, p.lpc, ckpt, rT, yT, uT, flags);
         DHTS_C_DISPATCH(p, CALL)
 #undef CALL
     }
@@ -781,29 +848,41 @@ template <typename T> static long long rollout_scratch_elems(int B, int N, int K
 }
 
 template <typename T>
-static int rollout_bwd(const T* ckpt, const T* u0, const T* ghost, const T* dx, const T* umax, T dt, int B, int N,
-                       int steps, int K, const T* rT, const T* yT, const T* g_rT, const T* g_yT, const T* g_uT,
-                       T* scratch, long long scratch_elems, T* g_r0, T* g_y0, T* g_ghost, int* flags,
-                       cudaStream_t st) {
-    if (!ckpt || !ghost || !dx || !umax || !g_r0 || !g_y0 || !flags || (!scratch && K > 1) || B < 0 || N < 1 || steps < 0 || K < 1)
+static int rollout_bwd(const T* ckpt, const T* u0, const T* ghost, const T* ghost_t, const T* dx, const T* umax, T dt, int B,
+                       int N, int steps, int K, const T* rT, const T* yT, const T* g_rT, const T* g_yT, const T* g_uT,
+                       const T* g_hist, T* scratch, long long scratch_elems, T* g_r0, T* g_y0, T* g_ghost, T* g_ghost_t,
+                       int* flags, cudaStream_t st) {
+    if (!ckpt || (!ghost && !ghost_t) || !dx || !umax || !g_r0 || !g_y0 || !flags || (!scratch && K > 1) || B < 0 || N < 1 || steps < 0 || K < 1)
         return DHTS_ERR_INVALID;
+    const bool ext = ghost_t || g_hist;
+    if (ext && K != 1) return DHTS_ERR_INVALID;        // per-step ghosts / per-step adjoints need every state stored
     if (g_uT && (!rT || !yT)) return DHTS_ERR_INVALID;
     if (B == 0) return DHTS_OK;
     RegPlan p;
     int rc = plan_reg<T>(B, N, true, &p);
     if (rc) return rc;
     if (p.C > 1 && !(al16(ckpt) && al16(u0) && al16(scratch) && al16(g_r0) && al16(g_y0))) return DHTS_ERR_UNSUPPORTED;
-    set_mode<T>(&p, K, al16(ckpt));
+    set_mode<T>(&p, K, al16(ckpt) && !ext);
+    if (ext && p.C > 1 && !al16(g_hist)) return DHTS_ERR_UNSUPPORTED;
     int grid = bwd_grid_r<T>(p);
     if (K > 1 && (long long)grid * K * 2 * p.lpc * N > scratch_elems) return DHTS_ERR_INVALID;
+    if (ext) {
+#define CALL(CC, MB)                                                                                                   \
+    arz_rollout_bwd_reg_kernel<T, CC, MB, 1, true><<<grid, p.threads, p.smem, st>>>(                                   \
+        ckpt, u0, ghost_t ? nullptr : ghost, ghost_t, g_hist, g_ghost_t, dx, umax, dt, B, N, steps, K, p.lpc, rT, yT,  \
+        g_rT, g_yT, g_uT, scratch, g_r0, g_y0, g_ghost, flags, 0);
+        DHTS_C_DISPATCH(p, CALL)
+#undef CALL
+        return status_r();
+    }
 #define CALLM(CC, MB, MD)                                                                                              \
     {                                                                                                                  \
         if (p.smem > 48 * 1024)                                                                                        \
             cudaFuncSetAttribute(arz_rollout_bwd_reg_kernel<T, CC, MB, MD>,                                            \
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);                            \
         arz_rollout_bwd_reg_kernel<T, CC, MB, MD><<<grid, p.threads, p.smem, st>>>(                                    \
-            ckpt, u0, ghost, dx, umax, dt, B, N, steps, K, p.lpc, rT, yT, g_rT, g_yT, g_uT, scratch, g_r0, g_y0,       \
-            g_ghost, flags, p.ring_ns);                                                                                \
+            ckpt, u0, ghost, nullptr, nullptr, nullptr, dx, umax, dt, B, N, steps, K, p.lpc, rT, yT, g_rT, g_yT, g_uT, \
+            scratch, g_r0, g_y0, g_ghost, flags, p.ring_ns);                                                           \
     }
     DHTS_CM_DISPATCH(p)
 #undef CALLM
@@ -813,22 +892,25 @@ static int rollout_bwd(const T* ckpt, const T* u0, const T* ghost, const T* dx, 
 }  // namespace dhts
 
 #define DHTS_ARZ_ROLLOUT_API(SUF, T)                                                                                   \
-    DHTS_EXPORT int dhts_arz_rollout_fwd_##SUF(const T* r0, const T* y0, const T* u0, const T* ghost, const T* dx,     \
-                                               const T* umax, T dt, int B, int N, int steps, int ckpt_every, T* ckpt,  \
-                                               T* rT, T* yT, T* uT, int* flags, void* stream) {                        \
-        return dhts::rollout_fwd<T>(r0, y0, u0, ghost, dx, umax, dt, B, N, steps, ckpt_every, ckpt, rT, yT, uT, flags, \
-                                    (cudaStream_t)stream);                                                             \
+    DHTS_EXPORT int dhts_arz_rollout_fwd_##SUF(const T* r0, const T* y0, const T* u0, const T* ghost, const T* ghost_t, \
+                                               const T* dx, const T* umax, T dt, int B, int N, int steps,              \
+                                               int ckpt_every, T* ckpt, T* rT, T* yT, T* uT, int* flags,               \
+                                               void* stream) {                                                         \
+        return dhts::rollout_fwd<T>(r0, y0, u0, ghost, ghost_t, dx, umax, dt, B, N, steps, ckpt_every, ckpt, rT, yT,   \
+                                    uT, flags, (cudaStream_t)stream);                                                  \
     }                                                                                                                  \
     DHTS_EXPORT long long dhts_arz_rollout_scratch_elems_##SUF(int B, int N, int ckpt_every) {                         \
         return dhts::rollout_scratch_elems<T>(B, N, ckpt_every);                                                       \
     }                                                                                                                  \
-    DHTS_EXPORT int dhts_arz_rollout_bwd_##SUF(const T* ckpt, const T* u0, const T* ghost, const T* dx, const T* umax, \
-                                               T dt, int B, int N, int steps, int ckpt_every, const T* rT,             \
-                                               const T* yT, const T* g_rT, const T* g_yT, const T* g_uT, T* scratch,   \
-                                               long long scratch_elems, T* g_r0, T* g_y0, T* g_ghost, int* flags,      \
-                                               void* stream) {                                                         \
-        return dhts::rollout_bwd<T>(ckpt, u0, ghost, dx, umax, dt, B, N, steps, ckpt_every, rT, yT, g_rT, g_yT, g_uT,  \
-                                    scratch, scratch_elems, g_r0, g_y0, g_ghost, flags, (cudaStream_t)stream);         \
+    DHTS_EXPORT int dhts_arz_rollout_bwd_##SUF(const T* ckpt, const T* u0, const T* ghost, const T* ghost_t,           \
+                                               const T* dx, const T* umax, T dt, int B, int N, int steps,              \
+                                               int ckpt_every, const T* rT, const T* yT, const T* g_rT,                \
+                                               const T* g_yT, const T* g_uT, const T* g_hist, T* scratch,              \
+                                               long long scratch_elems, T* g_r0, T* g_y0, T* g_ghost, T* g_ghost_t,    \
+                                               int* flags, void* stream) {                                             \
+        return dhts::rollout_bwd<T>(ckpt, u0, ghost, ghost_t, dx, umax, dt, B, N, steps, ckpt_every, rT, yT, g_rT,     \
+                                    g_yT, g_uT, g_hist, scratch, scratch_elems, g_r0, g_y0, g_ghost, g_ghost_t, flags, \
+                                    (cudaStream_t)stream);                                                             \
     }
 
 DHTS_ARZ_ROLLOUT_API(f64, double)

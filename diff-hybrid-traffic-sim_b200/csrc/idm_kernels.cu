@@ -187,8 +187,9 @@ __device__ __forceinline__ int lane_step(WarpLane<T, VPT>& w, T head_dp, T head_
 template <typename T, int VPT>
 __global__ void __launch_bounds__(IDM_ROLL_BLOCK)
 idm_rollout_fwd_kernel(const T* __restrict__ p0, const T* __restrict__ v0, const T* __restrict__ params,
-                       const int* __restrict__ lane_off, const T* __restrict__ head, T dt, int V, int L, int steps,
-                       int K, T* __restrict__ ckpt, T* __restrict__ pT, T* __restrict__ vT, int* __restrict__ flags) {
+                       const int* __restrict__ lane_off, const T* __restrict__ head, const T* __restrict__ head_t, T dt,
+                       int V, int L, int steps, int K, T* __restrict__ ckpt, T* __restrict__ pT, T* __restrict__ vT,
+                       int* __restrict__ flags) {
     const unsigned lane = threadIdx.x & 31;
     const int wid = (blockIdx.x * IDM_ROLL_BLOCK + threadIdx.x) >> 5, nw = (gridDim.x * IDM_ROLL_BLOCK) >> 5;
     const T inv_dt = T(1) / dt;
@@ -198,8 +199,12 @@ idm_rollout_fwd_kernel(const T* __restrict__ p0, const T* __restrict__ v0, const
         if (n <= 0) continue;
         WarpLane<T, VPT> w;
         lane_load(w, p0, v0, params, V, o, n, lane);
-        const T hdp = head[2 * l], hdv = head[2 * l + 1];
+        // head deltas: one pair for the whole rollout, or one per step (head_t [steps][L][2], fetched a step ahead)
+        T hdp = head_t ? (steps > 0 ? head_t[2 * l] : T(0)) : head[2 * l];
+        T hdv = head_t ? (steps > 0 ? head_t[2 * l + 1] : T(0)) : head[2 * l + 1];
         for (int t = 0; t < steps; t++) {
+            T ndp = hdp, ndv = hdv;
+            if (head_t && t + 1 < steps) { const T* q = head_t + ((size_t)(t + 1) * L + l) * 2; ndp = q[0]; ndv = q[1]; }
             if (ckpt && t % K == 0) {
                 T* cp = ckpt + (size_t)(t / K) * 2 * V + o; T* cv = cp + V;
 #pragma unroll
@@ -207,6 +212,7 @@ idm_rollout_fwd_kernel(const T* __restrict__ p0, const T* __restrict__ v0, const
                     if (w.valid[m]) { cp[m * 32 + lane] = w.p[m]; cv[m * 32 + lane] = w.v[m]; }
             }
             ncol += lane_step(w, hdp, hdv, lane, dt, inv_dt);
+            hdp = ndp; hdv = ndv;
         }
 #pragma unroll
         for (int m = 0; m < VPT; m++)
@@ -218,9 +224,10 @@ idm_rollout_fwd_kernel(const T* __restrict__ p0, const T* __restrict__ v0, const
 template <typename T, int VPT>
 __global__ void __launch_bounds__(IDM_ROLL_BLOCK)
 idm_rollout_bwd_kernel(const T* __restrict__ ckpt, const T* __restrict__ params, const int* __restrict__ lane_off,
-                       const T* __restrict__ head, T dt, int V, int L, int steps, int K, const T* __restrict__ g_pT,
-                       const T* __restrict__ g_vT, T* __restrict__ g_p0, T* __restrict__ g_v0,
-                       T* __restrict__ g_head, int* __restrict__ flags) {
+                       const T* __restrict__ head, const T* __restrict__ head_t, T dt, int V, int L, int steps, int K,
+                       const T* __restrict__ g_pT, const T* __restrict__ g_vT, const T* __restrict__ g_hist,
+                       T* __restrict__ g_p0, T* __restrict__ g_v0, T* __restrict__ g_head, T* __restrict__ g_head_t,
+                       int* __restrict__ flags) {
     const unsigned lane = threadIdx.x & 31;
     const int wid = (blockIdx.x * IDM_ROLL_BLOCK + threadIdx.x) >> 5, nw = (gridDim.x * IDM_ROLL_BLOCK) >> 5;
     const T inv_dt = T(1) / dt;
@@ -229,8 +236,13 @@ idm_rollout_bwd_kernel(const T* __restrict__ ckpt, const T* __restrict__ params,
     T sp[IDM_KMAX][VPT], sv[IDM_KMAX][VPT];       // per-thread stash of the segment's states
     for (int l = wid; l < L; l += nw) {
         const int o = lane_off[l], n = lane_off[l + 1] - o;
-        if (n <= 0) { if (g_head && lane == 0) { g_head[2 * l] = T(0); g_head[2 * l + 1] = T(0); } continue; }
-        const T hdp = head[2 * l], hdv = head[2 * l + 1];
+        if (n <= 0) {
+            if (g_head && lane == 0) { g_head[2 * l] = T(0); g_head[2 * l + 1] = T(0); }
+            if (g_head_t)
+                for (int t = (int)lane; t < steps; t += 32) { g_head_t[((size_t)t * L + l) * 2] = T(0); g_head_t[((size_t)t * L + l) * 2 + 1] = T(0); }
+            continue;
+        }
+        T hdp = head_t ? T(0) : head[2 * l], hdv = head_t ? T(0) : head[2 * l + 1];
         WarpLane<T, VPT> w;
         T gp[VPT], gv[VPT], ghp = T(0), ghv = T(0);
 #pragma unroll
@@ -245,12 +257,14 @@ idm_rollout_bwd_kernel(const T* __restrict__ ckpt, const T* __restrict__ params,
             for (int k = 0; k < ks; k++) {
 #pragma unroll
                 for (int m = 0; m < VPT; m++) { sp[k][m] = w.p[m]; sv[k][m] = w.v[m]; }
+                if (head_t) { const T* q = head_t + ((size_t)(t0 + k) * L + l) * 2; hdp = q[0]; hdv = q[1]; }
                 if (k + 1 < ks) lane_step(w, hdp, hdv, lane, dt, inv_dt);
             }
             for (int k = ks - 1; k >= 0; k--) {
 #pragma unroll
                 for (int m = 0; m < VPT; m++) { w.p[m] = sp[k][m]; w.v[m] = sv[k][m]; }
                 T dp[VPT], dv[VPT], cpv[VPT], cvv[VPT], np_[VPT], nv_[VPT];
+                if (head_t) { const T* q = head_t + ((size_t)(t0 + k) * L + l) * 2; hdp = q[0]; hdv = q[1]; }
                 lane_deltas(w, hdp, hdv, lane, dp, dv);
 #pragma unroll
                 for (int m = 0; m < VPT; m++) {
@@ -271,6 +285,20 @@ idm_rollout_bwd_kernel(const T* __restrict__ ckpt, const T* __restrict__ params,
                     const T sv_ = (lane == 31) ? (m > 0 ? cvv[m > 0 ? m - 1 : 0] : T(0)) : cvv[m];
                     const T fp = __shfl_sync(0xffffffffu, sp_, (lane + 31) & 31), fv = __shfl_sync(0xffffffffu, sv_, (lane + 31) & 31);
                     if (w.valid[m]) { gp[m] = np_[m] + fp; gv[m] = nv_[m] + fv; }
+                }
+                if (g_head_t) {       // per-step head deltas: this step's adjoint leaves, the accumulator restarts
+                    bool own = false;
+#pragma unroll
+                    for (int m = 0; m < VPT; m++) own |= w.head[m];
+                    if (own) { T* q = g_head_t + ((size_t)(t0 + k) * L + l) * 2; q[0] = ghp; q[1] = ghv; }
+                    bad |= t_isnan(ghp) || t_isnan(ghv);
+                    ghp = T(0); ghv = T(0);
+                }
+                if (g_hist) {         // loss terms on the state before this step
+                    const T* q = g_hist + (size_t)(t0 + k) * 2 * V + o;
+#pragma unroll
+                    for (int m = 0; m < VPT; m++)
+                        if (w.valid[m]) { gp[m] += q[m * 32 + lane]; gv[m] += q[V + m * 32 + lane]; }
                 }
             }
         }
@@ -340,31 +368,33 @@ static int idm_step_bwd(const T* p, const T* v, const T* params, const int* lane
     else return DHTS_ERR_UNSUPPORTED;
 
 template <typename T>
-static int idm_rollout_fwd(const T* p0, const T* v0, const T* params, const int* lane_off, const T* head, T dt, int V,
-                           int L, int max_lane, int steps, int K, T* ckpt, T* pT, T* vT, int* flags, cudaStream_t st) {
-    if (!p0 || !v0 || !params || !lane_off || !head || !pT || !vT || !flags || V < 0 || L < 0 || steps < 0 || max_lane < 0)
+static int idm_rollout_fwd(const T* p0, const T* v0, const T* params, const int* lane_off, const T* head, const T* head_t,
+                           T dt, int V, int L, int max_lane, int steps, int K, T* ckpt, T* pT, T* vT, int* flags,
+                           cudaStream_t st) {
+    if (!p0 || !v0 || !params || !lane_off || (!head && !head_t) || !pT || !vT || !flags || V < 0 || L < 0 || steps < 0 || max_lane < 0)
         return DHTS_ERR_INVALID;
     if (ckpt && K < 1) return DHTS_ERR_INVALID;
     if (V == 0 || L == 0) return DHTS_OK;
     int grid = idm_grid(L);
     if (K < 1) K = 1;
-#define CALL(VPT) idm_rollout_fwd_kernel<T, VPT><<<grid, IDM_ROLL_BLOCK, 0, st>>>(p0, v0, params, lane_off, head, dt, V, L, steps, K, ckpt, pT, vT, flags);
+#define CALL(VPT) idm_rollout_fwd_kernel<T, VPT><<<grid, IDM_ROLL_BLOCK, 0, st>>>(p0, v0, params, lane_off, head, head_t, dt, V, L, steps, K, ckpt, pT, vT, flags);
     DHTS_VPT_DISPATCH(max_lane, CALL)
 #undef CALL
     return last_status_idm();
 }
 
 template <typename T>
-static int idm_rollout_bwd(const T* ckpt, const T* params, const int* lane_off, const T* head, T dt, int V, int L,
-                           int max_lane, int steps, int K, const T* g_pT, const T* g_vT, T* g_p0, T* g_v0, T* g_head,
-                           int* flags, cudaStream_t st) {
-    if (!ckpt || !params || !lane_off || !head || !g_pT || !g_vT || !g_p0 || !g_v0 || !flags || V < 0 || L < 0 ||
+static int idm_rollout_bwd(const T* ckpt, const T* params, const int* lane_off, const T* head, const T* head_t, T dt, int V,
+                           int L, int max_lane, int steps, int K, const T* g_pT, const T* g_vT, const T* g_hist, T* g_p0,
+                           T* g_v0, T* g_head, T* g_head_t, int* flags, cudaStream_t st) {
+    if (!ckpt || !params || !lane_off || (!head && !head_t) || !g_pT || !g_vT || !g_p0 || !g_v0 || !flags || V < 0 || L < 0 ||
         steps < 0 || max_lane < 0 || K < 1)
         return DHTS_ERR_INVALID;
+    if ((g_head_t && !head_t) || (g_hist && K != 1)) return DHTS_ERR_INVALID;      // g_hist is laid out like ckpt with K = 1
     if (K > IDM_KMAX) return DHTS_ERR_UNSUPPORTED;
     if (L == 0) return DHTS_OK;
     int grid = idm_grid(L);
-#define CALL(VPT) idm_rollout_bwd_kernel<T, VPT><<<grid, IDM_ROLL_BLOCK, 0, st>>>(ckpt, params, lane_off, head, dt, V, L, steps, K, g_pT, g_vT, g_p0, g_v0, g_head, flags);
+#define CALL(VPT) idm_rollout_bwd_kernel<T, VPT><<<grid, IDM_ROLL_BLOCK, 0, st>>>(ckpt, params, lane_off, head, head_t, dt, V, L, steps, K, g_pT, g_vT, g_hist, g_p0, g_v0, head_t ? nullptr : g_head, g_head_t, flags);
     DHTS_VPT_DISPATCH(max_lane, CALL)
 #undef CALL
     return last_status_idm();
@@ -386,17 +416,19 @@ static int idm_rollout_bwd(const T* ckpt, const T* params, const int* lane_off, 
                                      flags, (cudaStream_t)stream);                                                     \
     }                                                                                                                  \
     DHTS_EXPORT int dhts_idm_rollout_fwd_##SUF(const T* p0, const T* v0, const T* params, const int* lane_off,         \
-                                               const T* head, T dt, int V, int L, int max_lane, int steps,             \
-                                               int ckpt_every, T* ckpt, T* pT, T* vT, int* flags, void* stream) {      \
-        return dhts::idm_rollout_fwd<T>(p0, v0, params, lane_off, head, dt, V, L, max_lane, steps, ckpt_every, ckpt,   \
-                                        pT, vT, flags, (cudaStream_t)stream);                                          \
+                                               const T* head, const T* head_t, T dt, int V, int L, int max_lane,       \
+                                               int steps, int ckpt_every, T* ckpt, T* pT, T* vT, int* flags,           \
+                                               void* stream) {                                                         \
+        return dhts::idm_rollout_fwd<T>(p0, v0, params, lane_off, head, head_t, dt, V, L, max_lane, steps, ckpt_every, \
+                                        ckpt, pT, vT, flags, (cudaStream_t)stream);                                    \
     }                                                                                                                  \
     DHTS_EXPORT int dhts_idm_rollout_bwd_##SUF(const T* ckpt, const T* params, const int* lane_off, const T* head,     \
-                                               T dt, int V, int L, int max_lane, int steps, int ckpt_every,            \
-                                               const T* g_pT, const T* g_vT, T* g_p0, T* g_v0, T* g_head, int* flags,  \
-                                               void* stream) {                                                         \
-        return dhts::idm_rollout_bwd<T>(ckpt, params, lane_off, head, dt, V, L, max_lane, steps, ckpt_every, g_pT,     \
-                                        g_vT, g_p0, g_v0, g_head, flags, (cudaStream_t)stream);                        \
+                                               const T* head_t, T dt, int V, int L, int max_lane, int steps,           \
+                                               int ckpt_every, const T* g_pT, const T* g_vT, const T* g_hist,          \
+                                               T* g_p0, T* g_v0, T* g_head, T* g_head_t, int* flags, void* stream) {   \
+        return dhts::idm_rollout_bwd<T>(ckpt, params, lane_off, head, head_t, dt, V, L, max_lane, steps, ckpt_every,   \
+                                        g_pT, g_vT, g_hist, g_p0, g_v0, g_head, g_head_t, flags,                       \
+                                        (cudaStream_t)stream);                                                         \
     }
 
 // C ABI

@@ -39,11 +39,15 @@ def arz_step(r_pad, y_pad, u_pad, dx, umax, dt, flags, ueq_pad=None, want_case=F
                            flags.t, want_case)
 
 
-def arz_rollout(r0, u0, ghost_r, ghost_u, dx, umax, dt, steps, ckpt_every=32, flags=None, ckpt_buffer=None):
-    """`steps` x RoadNetwork.forward over B disconnected dMacroLanes with static ghost cells, i.e. the
-    loop of example/inverse/_inverse.py:91-99 for example/inverse/macro.py, batched:
+def arz_rollout(r0, u0, ghost_r, ghost_u, dx, umax, dt, steps, ckpt_every=32, flags=None, ckpt_buffer=None,
+                return_history=False):
+    """`steps` x RoadNetwork.forward over B disconnected dMacroLanes, i.e. the loop of
+    example/inverse/_inverse.py:91-99 for example/inverse/macro.py, batched:
     set_state_vector_u(r0, u0) -> steps x (boundary, forward, update_state) -> get_state_vector().
-    r0, u0 [B, N]; ghost_r, ghost_u [B, 2] (left, right).  Returns (rT, yT, uT) [B, N].
+    r0, u0 [B, N]; ghost_r, ghost_u [B, 2] (left, right) static ghost cells, or [steps, B, 2]: one pair per step
+    (what a lane inside a network sees, road_network.py:364-387; needs ckpt_every = 1).  Returns (rT, yT, uT) [B, N];
+    with return_history=True (ckpt_every = 1) also (r_hist, y_hist) [steps, B, N], the state BEFORE every step, both
+    differentiable: a loss may read the lane at every step and the adjoint kernel injects its gradient step by step.
     ckpt_buffer: optional flat tensor the state checkpoints are written into instead of a fresh allocation;
     it must stay untouched until this rollout's backward has run (see arz_rollout_plan)."""
     B, N = r0.shape
@@ -53,17 +57,25 @@ def arz_rollout(r0, u0, ghost_r, ghost_u, dx, umax, dt, steps, ckpt_every=32, fl
     y0 = compute_y(r0, u0, um)                       # set_r_u, _arz.py:82-86 (autograd, true derivative)
     ghost = torch.stack([ghost_r, compute_y(ghost_r, ghost_u, um), ghost_u.detach()], dim=-1)   # from_r_u, :74-80
     try:
-        return ArzRolloutFn.apply(r0, y0, u0.detach(), ghost, dxl, uml, dt, steps, ckpt_every, flags.t, ckpt_buffer)
+        out = ArzRolloutFn.apply(r0, y0, u0.detach(), ghost, dxl, uml, dt, steps, ckpt_every, flags.t, ckpt_buffer,
+                                 bool(return_history))
+        if return_history:
+            return out[0], out[1], out[2], out[3][:, 0], out[3][:, 1]
+        return out
     except _lib.UnsupportedShape:
         pass
-    # lane too long for the smem-resident kernel: chain the tiled per-step kernels (still CUDA)
+    # lane too long for the register-resident kernel: chain the tiled per-step kernels (still CUDA)
     r, y, u = r0, y0, u0.detach()
-    g = ghost
-    for _ in range(int(steps)):
+    hist = []
+    for t in range(int(steps)):
+        g = ghost[t] if ghost.dim() == 4 else ghost
+        hist.append((r, y))
         r_pad = torch.cat([g[:, 0:1, 0], r, g[:, 1:2, 0]], dim=1)
         y_pad = torch.cat([g[:, 0:1, 1], y, g[:, 1:2, 1]], dim=1)
         u_pad = torch.cat([g[:, 0:1, 2], u.detach(), g[:, 1:2, 2]], dim=1)
         r, y, u = ArzStepFn.apply(r_pad, y_pad, u_pad, None, dxl, uml, dt, flags.t, False)
+    if return_history:
+        return r, y, u, torch.stack([h[0] for h in hist]), torch.stack([h[1] for h in hist])
     return r, y, u
 
 
@@ -71,12 +83,12 @@ def arz_rollout_state(r0, y0, u0, ghost, dx, umax, dt, steps, ckpt_every, flags)
     """The rollout operator on lane STATE as the lanes hold it: (r0, y0)[B, N] differentiable, u0 the speed stored on
     the cells (value only), ghost [B, 2, 3] = (r, y, u) per side, dx / umax [B].  Returns (rT, yT, uT).  What the
     drop-in network's deferred stepping calls (dropin/deferred.py)."""
-    return ArzRolloutFn.apply(r0, y0, u0.detach(), ghost, dx, umax, dt, steps, ckpt_every, flags.t, None)
+    return ArzRolloutFn.apply(r0, y0, u0.detach(), ghost, dx, umax, dt, steps, ckpt_every, flags.t, None, False)
 
 
 def idm_rollout_state(p0, v0, params, lane_off, head, dt, steps, ckpt_every, flags, max_lane):
     """The IDM rollout operator without the per-step fallback of `idm_rollout` (raises UnsupportedShape instead)."""
-    return IdmRolloutFn.apply(p0, v0, head, params, lane_off, max_lane, dt, steps, ckpt_every, flags.t)
+    return IdmRolloutFn.apply(p0, v0, head, params, lane_off, max_lane, dt, steps, ckpt_every, flags.t, False)
 
 
 def arz_rollout_plan(B, N, steps, dtype, device, mem_fraction=0.6, min_lanes=296):
@@ -107,21 +119,30 @@ def idm_step(p, v, params, lane_off, head, dt, flags, veh_lane=None, want_flags=
     return IdmStepFn.apply(p, v, head, params, lane_off, veh_lane, dt, flags.t, want_flags)
 
 
-def idm_rollout(p0, v0, params, lane_off, head, dt, steps, ckpt_every=32, flags=None, max_lane=None):
+def idm_rollout(p0, v0, params, lane_off, head, dt, steps, ckpt_every=32, flags=None, max_lane=None, return_history=False):
     """`steps` x RoadNetwork.forward over L independent dMicroLanes whose heads follow the ghost leader
     (head_position_delta, head_speed_delta): the loop of example/inverse/_inverse.py:91-99 for
-    example/inverse/micro.py, batched.  Returns (pT, vT) [V]."""
+    example/inverse/micro.py, batched.  head [L, 2], or [steps, L, 2] for one pair per step (needs no special
+    checkpointing).  Returns (pT, vT) [V]; with return_history=True (ckpt_every = 1) also (p_hist, v_hist) [steps, V],
+    the state BEFORE every step, differentiable (a loss may read the lanes at every step)."""
     flags = flags or _lib.Flags(p0.device)
     if max_lane is None:
         max_lane = int((lane_off[1:] - lane_off[:-1]).max().item()) if lane_off.numel() > 1 else 0
     try:
-        return IdmRolloutFn.apply(p0, v0, head, params, lane_off, max_lane, dt, steps, ckpt_every, flags.t)
+        out = IdmRolloutFn.apply(p0, v0, head, params, lane_off, max_lane, dt, steps, ckpt_every, flags.t, bool(return_history))
+        if return_history:
+            return out[0], out[1], out[2][:, 0, :p0.numel()], out[2][:, 1, :p0.numel()]
+        return out
     except _lib.UnsupportedShape:
         pass
     veh_lane = csr_expand(lane_off, p0.numel())
     p, v = p0, v0
-    for _ in range(int(steps)):
-        p, v = IdmStepFn.apply(p, v, head, params, lane_off, veh_lane, dt, flags.t, False)
+    hist = []
+    for t in range(int(steps)):
+        hist.append((p, v))
+        p, v = IdmStepFn.apply(p, v, head[t] if head.dim() == 3 else head, params, lane_off, veh_lane, dt, flags.t, False)
+    if return_history:
+        return p, v, torch.stack([h[0] for h in hist]), torch.stack([h[1] for h in hist])
     return p, v
 
 

@@ -105,18 +105,28 @@ def _lease_arena(buf):
 
 
 class ArzRolloutFn(torch.autograd.Function):
-    """(r0, y0)[B,N], ghost[B,2,3] -> (rT, yT, uT)[B,N] after `steps` fused steps with static ghosts."""
+    """(r0, y0)[B,N], ghost -> (rT, yT, uT)[B,N] (+ hist) after `steps` fused steps.
+
+    ghost [B,2,3]: static ghost cells (r, y, u); ghost [steps,B,2,3]: one pair of ghost cells PER STEP (a lane inside
+    a network, road_network.py:364-387).  want_hist (needs ckpt_every = 1): a fourth output hist [steps,2,B,N], the
+    (r, y) state BEFORE every step (hist[0] = the input) -- the kernels' checkpoint tensor itself -- so that a loss
+    may read the lane at every step; its gradient is injected step by step in the adjoint kernel."""
 
     @staticmethod
-    def forward(ctx, r0, y0, u0, ghost, dx, umax, dt, steps, ckpt_every, flags, ckpt_buffer=None):
+    def forward(ctx, r0, y0, u0, ghost, dx, umax, dt, steps, ckpt_every, flags, ckpt_buffer=None, want_hist=False):
         dev = _lib.require_cuda(r0, y0, u0, ghost, dx, umax, flags)
         r0, y0, u0, ghost, dx, umax = map(_c, (r0, y0, u0, ghost, dx, umax))
         B, N = r0.shape
         dt_, steps, K = float(dt), int(steps), max(1, int(ckpt_every))
+        tv = ghost.dim() == 4
+        if tv:
+            assert ghost.shape == (steps, B, 2, 3), "per-step ghosts are [steps, B, 2, 3]"
+        if (tv or want_hist) and K != 1:
+            raise ValueError("per-step ghosts and the state history need ckpt_every = 1 (every state stored)")
         need_grad = any(ctx.needs_input_grad[i] for i in (0, 1, 3))
         S = (steps + K - 1) // K
         ckpt = None
-        if need_grad:
+        if need_grad or want_hist:
             n = S * 2 * B * N
             if ckpt_buffer is not None:      # caller-owned arena, reused across sequential rollouts (lane chunks)
                 if ckpt_buffer.dtype != r0.dtype or ckpt_buffer.device != dev or ckpt_buffer.numel() < n:
@@ -127,40 +137,45 @@ class ArzRolloutFn(torch.autograd.Function):
                 ckpt = torch.empty((S, 2, B, N), dtype=r0.dtype, device=dev)
         rT = torch.empty_like(r0); yT = torch.empty_like(r0); uT = torch.empty_like(r0)
         with torch.cuda.device(dev):
-            check(_fn("arz_rollout_fwd", r0.dtype)(ptr(r0), ptr(y0), ptr(u0), ptr(ghost), ptr(dx), ptr(umax),
+            check(_fn("arz_rollout_fwd", r0.dtype)(ptr(r0), ptr(y0), ptr(u0), ptr(None if tv else ghost),
+                                                   ptr(ghost if tv else None), ptr(dx), ptr(umax),
                                                    creal(r0.dtype, dt_), B, N, steps, K, ptr(ckpt), ptr(rT), ptr(yT),
                                                    ptr(uT), ptr(flags), stream_ptr(dev)), "dhts_arz_rollout_fwd")
         if need_grad:
             ctx.save_for_backward(ckpt, u0, ghost, dx, umax, rT, yT)
         ctx.flags = flags
-        ctx.cfg = (dt_, steps, K, B, N)
+        ctx.cfg = (dt_, steps, K, B, N, tv, bool(want_hist))
+        if want_hist:
+            return rT, yT, uT, ckpt
         return rT, yT, uT
 
     @staticmethod
-    def backward(ctx, g_rT, g_yT, g_uT):
+    def backward(ctx, g_rT, g_yT, g_uT, g_hist=None):
         ckpt, u0, ghost, dx, umax, rT, yT = ctx.saved_tensors
         flags = ctx.flags
-        dt_, steps, K, B, N = ctx.cfg
+        dt_, steps, K, B, N, tv, want_hist = ctx.cfg
         dev, dtype = ghost.device, ghost.dtype
-        g_rT, g_yT, g_uT = map(_c, (g_rT, g_yT, g_uT))
+        g_rT, g_yT, g_uT, g_hist = map(_c, (g_rT, g_yT, g_uT, g_hist))
         g_r0 = torch.empty((B, N), dtype=dtype, device=dev)
         g_y0 = torch.empty_like(g_r0)
-        g_gh = torch.empty((B, 2, 2), dtype=dtype, device=dev)
+        g_gh = torch.empty((steps, B, 2, 2) if tv else (B, 2, 2), dtype=dtype, device=dev)
         with torch.cuda.device(dev):
             n = _fn("arz_rollout_scratch_elems", dtype)(B, N, K)
             if n < 0:
                 raise _lib.UnsupportedShape("dhts_arz_rollout_bwd: lane does not fit the fused kernel")
             scratch = torch.empty((max(int(n), 1),), dtype=dtype, device=dev)
-            check(_fn("arz_rollout_bwd", dtype)(ptr(ckpt), ptr(u0), ptr(ghost), ptr(dx), ptr(umax), creal(dtype, dt_),
-                                                B, N, steps, K, ptr(rT), ptr(yT), ptr(g_rT), ptr(g_yT), ptr(g_uT),
-                                                ptr(scratch), ctypes.c_longlong(int(n)), ptr(g_r0), ptr(g_y0),
-                                                ptr(g_gh), ptr(flags), stream_ptr(dev)), "dhts_arz_rollout_bwd")
+            check(_fn("arz_rollout_bwd", dtype)(ptr(ckpt), ptr(u0), ptr(None if tv else ghost), ptr(ghost if tv else None),
+                                                ptr(dx), ptr(umax), creal(dtype, dt_), B, N, steps, K, ptr(rT), ptr(yT),
+                                                ptr(g_rT), ptr(g_yT), ptr(g_uT), ptr(g_hist), ptr(scratch),
+                                                ctypes.c_longlong(int(n)), ptr(g_r0), ptr(g_y0),
+                                                ptr(None if tv else g_gh), ptr(g_gh if tv else None), ptr(flags),
+                                                stream_ptr(dev)), "dhts_arz_rollout_bwd")
         lease = getattr(ctx, "lease", None)
         if lease is not None:
             lease.active = False          # the arena has been read: the next rollout may overwrite it
-        g_ghost = torch.zeros((B, 2, 3), dtype=dtype, device=dev)
-        g_ghost[:, :, :2] = g_gh          # ghost u is a value-only input
-        return g_r0, g_y0, None, g_ghost, None, None, None, None, None, None, None
+        g_ghost = torch.zeros(ghost.shape, dtype=dtype, device=dev)
+        g_ghost[..., :2] = g_gh           # ghost u is a value-only input
+        return g_r0, g_y0, None, g_ghost, None, None, None, None, None, None, None, None
 
 
 def csr_expand(lane_off: torch.Tensor, V: int) -> torch.Tensor:
@@ -214,46 +229,60 @@ class IdmStepFn(torch.autograd.Function):
 
 
 class IdmRolloutFn(torch.autograd.Function):
-    """(p0, v0)[V], head[L,2] -> (pT, vT)[V] after `steps` fused steps (one warp per lane)."""
+    """(p0, v0)[V], head -> (pT, vT)[V] (+ hist) after `steps` fused steps (one warp per lane).
+
+    head [L,2]: one (head_position_delta, head_speed_delta) pair per lane for the whole rollout; head [steps,L,2]: one
+    pair PER STEP (inside a network setup_micro_boundary rewrites them every step, road_network.py:429-580).
+    want_hist (ckpt_every = 1): a third output hist [steps,2,V], (p, v) BEFORE every step, differentiable."""
 
     @staticmethod
-    def forward(ctx, p0, v0, head, params, lane_off, max_lane, dt, steps, ckpt_every, flags):
+    def forward(ctx, p0, v0, head, params, lane_off, max_lane, dt, steps, ckpt_every, flags, want_hist=False):
         dev = _lib.require_cuda(p0, v0, head, params, lane_off, flags)
         p0, v0, head, params, lane_off = map(_c, (p0, v0, head, params, lane_off))
         V, L = p0.numel(), lane_off.numel() - 1
         lib = _lib.load()
         dt_, steps = float(dt), int(steps)
         K = max(1, min(int(ckpt_every), lib.dhts_idm_rollout_max_ckpt_every()))
+        tv = head.dim() == 3
+        if tv:
+            assert head.shape == (steps, L, 2), "per-step head deltas are [steps, L, 2]"
+        if want_hist and K != 1:
+            raise ValueError("the state history needs ckpt_every = 1 (every state stored)")
         need_grad = any(ctx.needs_input_grad[i] for i in (0, 1, 2))
         S = (steps + K - 1) // K
-        ckpt = torch.empty((S, 2, max(V, 1)), dtype=p0.dtype, device=dev) if need_grad else None
+        ckpt = torch.empty((S, 2, max(V, 1)), dtype=p0.dtype, device=dev) if (need_grad or want_hist) else None
         pT = torch.empty_like(p0); vT = torch.empty_like(p0)
         with torch.cuda.device(dev):
-            check(_fn("idm_rollout_fwd", p0.dtype)(ptr(p0), ptr(v0), ptr(params), ptr(lane_off), ptr(head),
-                                                   creal(p0.dtype, dt_), V, L, int(max_lane), steps, K, ptr(ckpt),
-                                                   ptr(pT), ptr(vT), ptr(flags), stream_ptr(dev)),
+            check(_fn("idm_rollout_fwd", p0.dtype)(ptr(p0), ptr(v0), ptr(params), ptr(lane_off), ptr(None if tv else head),
+                                                   ptr(head if tv else None), creal(p0.dtype, dt_), V, L, int(max_lane),
+                                                   steps, K, ptr(ckpt), ptr(pT), ptr(vT), ptr(flags), stream_ptr(dev)),
                   "dhts_idm_rollout_fwd")
         if need_grad:
             ctx.save_for_backward(ckpt, head, params, lane_off)
         ctx.flags = flags
-        ctx.cfg = (dt_, steps, K, V, L, int(max_lane))
+        ctx.cfg = (dt_, steps, K, V, L, int(max_lane), tv)
+        if want_hist:
+            return pT, vT, ckpt
         return pT, vT
 
     @staticmethod
-    def backward(ctx, g_pT, g_vT):
+    def backward(ctx, g_pT, g_vT, g_hist=None):
         ckpt, head, params, lane_off = ctx.saved_tensors
         flags = ctx.flags
-        dt_, steps, K, V, L, max_lane = ctx.cfg
+        dt_, steps, K, V, L, max_lane, tv = ctx.cfg
         dev, dtype = head.device, head.dtype
         z = lambda g: torch.zeros((V,), dtype=dtype, device=dev) if g is None else g.contiguous()
         g_pT, g_vT = z(g_pT), z(g_vT)
+        g_hist = _c(g_hist)
         g_p0 = torch.empty((V,), dtype=dtype, device=dev); g_v0 = torch.empty_like(g_p0)
         g_head = torch.zeros_like(head)
         with torch.cuda.device(dev):
-            check(_fn("idm_rollout_bwd", dtype)(ptr(ckpt), ptr(params), ptr(lane_off), ptr(head), creal(dtype, dt_), V,
-                                                L, max_lane, steps, K, ptr(g_pT), ptr(g_vT), ptr(g_p0), ptr(g_v0),
-                                                ptr(g_head), ptr(flags), stream_ptr(dev)), "dhts_idm_rollout_bwd")
-        return g_p0, g_v0, g_head, None, None, None, None, None, None, None
+            check(_fn("idm_rollout_bwd", dtype)(ptr(ckpt), ptr(params), ptr(lane_off), ptr(None if tv else head),
+                                                ptr(head if tv else None), creal(dtype, dt_), V, L, max_lane, steps, K,
+                                                ptr(g_pT), ptr(g_vT), ptr(g_hist), ptr(g_p0), ptr(g_v0),
+                                                ptr(None if tv else g_head), ptr(g_head if tv else None), ptr(flags),
+                                                stream_ptr(dev)), "dhts_idm_rollout_bwd")
+        return g_p0, g_v0, g_head, None, None, None, None, None, None, None, None
 
 
 class MacroToMicroFn(torch.autograd.Function):

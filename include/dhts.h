@@ -110,33 +110,41 @@ int dhts_arz_step_bwd_f32(const float* r_pad, const float* y_pad, const float* u
  * dhts_idm_rollout_max_ckpt_every() = 32, with the same fallback.
  */
 int dhts_arz_rollout_fwd_f64(const double* r0, const double* y0, const double* u0, const double* ghost,
-                             const double* dx, const double* umax, double dt, int B, int N, int steps, int ckpt_every,
-                             double* ckpt, double* rT, double* yT, double* uT, int* flags, void* stream);
-int dhts_arz_rollout_fwd_f32(const float* r0, const float* y0, const float* u0, const float* ghost, const float* dx,
-                             const float* umax, float dt, int B, int N, int steps, int ckpt_every, float* ckpt,
-                             float* rT, float* yT, float* uT, int* flags, void* stream);
+                             const double* ghost_t, const double* dx, const double* umax, double dt, int B, int N,
+                             int steps, int ckpt_every, double* ckpt, double* rT, double* yT, double* uT, int* flags,
+                             void* stream);
+int dhts_arz_rollout_fwd_f32(const float* r0, const float* y0, const float* u0, const float* ghost,
+                             const float* ghost_t, const float* dx, const float* umax, float dt, int B, int N,
+                             int steps, int ckpt_every, float* ckpt, float* rT, float* yT, float* uT, int* flags,
+                             void* stream);
 
-/* Scratch (in elements of T) the backward rollout needs for (B, N, ckpt_every);
- * -1 if unsupported.  Depends on the current device's SM count. */
+/* Adjoint of the rollout: the chain of dMacroForwardLayer.backward calls autograd makes for the T steps
+ * (road/lane/dmacro_lane.py:277-310), flux-difference form, no stored Jacobian band.
+ *   ckpt                    what the forward call wrote (same ckpt_every)
+ *   rT, yT                  final state (only read when g_uT is given: uT = compute_u(rT, yT))
+ *   g_rT, g_yT, g_uT [B][N] adjoint of the final state, each may be NULL
+ *   scratch                 dhts_arz_rollout_scratch_elems(B, N, ckpt_every) elements (0 when ckpt_every = 1)
+ *   g_r0, g_y0 [B][N]       adjoint of the initial (r, y)
+ *   g_ghost [B][2][2] or NULL  adjoint of the static ghosts' (r, y), summed over the steps
+ * Per-step coupling (both need ckpt_every = 1, i.e. ckpt IS the state history [steps][2][B][N]):
+ *   ghost_t [steps][B][2][3] or NULL  ghost (r, y, u) PER STEP instead of `ghost`: a lane inside a network gets new
+ *                           ghost cells every step (road/network/road_network.py:364-387); forward and adjoint
+ *   g_ghost_t [steps][B][2][2] or NULL  their adjoints, step by step
+ *   g_hist [steps][2][B][N] or NULL   adjoint of a loss that reads the state BEFORE every step (a per-step loss such as
+ *                           the ITSCP queue length, example/control/itscp/_env.py:662-742, on independent lanes)
+ */
+int dhts_arz_rollout_bwd_f64(const double* ckpt, const double* u0, const double* ghost, const double* ghost_t,
+                             const double* dx, const double* umax, double dt, int B, int N, int steps, int ckpt_every,
+                             const double* rT, const double* yT, const double* g_rT, const double* g_yT,
+                             const double* g_uT, const double* g_hist, double* scratch, long long scratch_elems,
+                             double* g_r0, double* g_y0, double* g_ghost, double* g_ghost_t, int* flags, void* stream);
+int dhts_arz_rollout_bwd_f32(const float* ckpt, const float* u0, const float* ghost, const float* ghost_t,
+                             const float* dx, const float* umax, float dt, int B, int N, int steps, int ckpt_every,
+                             const float* rT, const float* yT, const float* g_rT, const float* g_yT, const float* g_uT,
+                             const float* g_hist, float* scratch, long long scratch_elems, float* g_r0, float* g_y0,
+                             float* g_ghost, float* g_ghost_t, int* flags, void* stream);
 long long dhts_arz_rollout_scratch_elems_f64(int B, int N, int ckpt_every);
 long long dhts_arz_rollout_scratch_elems_f32(int B, int N, int ckpt_every);
-
-/* Adjoint through time: segments walked backwards, each recomputed from its
- * checkpoint, then the per-step VJP of dmacro_lane.py:277-310 applied.
- *   g_rT, g_yT, g_uT [B][N] (each may be NULL = zero); rT, yT needed iff g_uT
- *   g_r0, g_y0 [B][N]      adjoint of (r0, y0)
- *   g_ghost [B][2][2] or NULL  adjoint of the ghost (r, y), summed over steps
- */
-int dhts_arz_rollout_bwd_f64(const double* ckpt, const double* u0, const double* ghost, const double* dx,
-                             const double* umax, double dt, int B, int N, int steps, int ckpt_every, const double* rT,
-                             const double* yT, const double* g_rT, const double* g_yT, const double* g_uT,
-                             double* scratch, long long scratch_elems, double* g_r0, double* g_y0, double* g_ghost,
-                             int* flags, void* stream);
-int dhts_arz_rollout_bwd_f32(const float* ckpt, const float* u0, const float* ghost, const float* dx,
-                             const float* umax, float dt, int B, int N, int steps, int ckpt_every, const float* rT,
-                             const float* yT, const float* g_rT, const float* g_yT, const float* g_uT, float* scratch,
-                             long long scratch_elems, float* g_r0, float* g_y0, float* g_ghost, int* flags,
-                             void* stream);
 
 /* ---------------------------------------------------------------- IDM, one step
  * Forward half of dMicroForwardLayer (dmicro_lane.py:230-269 -> MicroLane.forward,
@@ -171,18 +179,24 @@ int dhts_idm_step_bwd_f32(const float* p, const float* v, const float* params, c
 int dhts_idm_rollout_max_lane(void);
 int dhts_idm_rollout_max_ckpt_every(void);
 int dhts_idm_rollout_fwd_f64(const double* p0, const double* v0, const double* params, const int* lane_off,
-                             const double* head, double dt, int V, int L, int max_lane, int steps, int ckpt_every,
-                             double* ckpt, double* pT, double* vT, int* flags, void* stream);
+                             const double* head, const double* head_t, double dt, int V, int L, int max_lane, int steps,
+                             int ckpt_every, double* ckpt, double* pT, double* vT, int* flags, void* stream);
 int dhts_idm_rollout_fwd_f32(const float* p0, const float* v0, const float* params, const int* lane_off,
-                             const float* head, float dt, int V, int L, int max_lane, int steps, int ckpt_every,
-                             float* ckpt, float* pT, float* vT, int* flags, void* stream);
+                             const float* head, const float* head_t, float dt, int V, int L, int max_lane, int steps,
+                             int ckpt_every, float* ckpt, float* pT, float* vT, int* flags, void* stream);
+/* Per-step coupling, as for the ARZ rollouts:
+ *   head_t [steps][L][2] or NULL    head deltas PER STEP instead of `head` (inside a network
+ *                                   RoadNetwork.setup_micro_boundary rewrites them before every step,
+ *                                   road/network/road_network.py:429-580); g_head_t [steps][L][2] their adjoints
+ *   g_hist [steps][2][V] or NULL    adjoint of a loss that reads (p, v) BEFORE every step; needs ckpt_every = 1 */
 int dhts_idm_rollout_bwd_f64(const double* ckpt, const double* params, const int* lane_off, const double* head,
-                             double dt, int V, int L, int max_lane, int steps, int ckpt_every, const double* g_pT,
-                             const double* g_vT, double* g_p0, double* g_v0, double* g_head, int* flags,
-                             void* stream);
-int dhts_idm_rollout_bwd_f32(const float* ckpt, const float* params, const int* lane_off, const float* head, float dt,
-                             int V, int L, int max_lane, int steps, int ckpt_every, const float* g_pT,
-                             const float* g_vT, float* g_p0, float* g_v0, float* g_head, int* flags, void* stream);
+                             const double* head_t, double dt, int V, int L, int max_lane, int steps, int ckpt_every,
+                             const double* g_pT, const double* g_vT, const double* g_hist, double* g_p0, double* g_v0,
+                             double* g_head, double* g_head_t, int* flags, void* stream);
+int dhts_idm_rollout_bwd_f32(const float* ckpt, const float* params, const int* lane_off, const float* head,
+                             const float* head_t, float dt, int V, int L, int max_lane, int steps, int ckpt_every,
+                             const float* g_pT, const float* g_vT, const float* g_hist, float* g_p0, float* g_v0,
+                             float* g_head, float* g_head_t, int* flags, void* stream);
 
 /* ---------------------------------------------------------------- macro <-> micro exchange (per junction)
  * macro -> micro, road/network/conversion.py:15-73 (with MacroLane.add_flux_capacitor,

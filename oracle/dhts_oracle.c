@@ -359,11 +359,31 @@ void orc_dy_dru(double r, double u, double umax, double *dy_dr, double *dy_du) {
  * hist (optional) [T+1][B][N][2] receives every (r,y) state.
  * Returns number of lanes that tripped the CFL assert.
  */
+/* ghost_t  optional [T][B][2][2]: (r, u) of the two ghost cells PER STEP (a lane inside a network gets new ghosts every
+ *          step, road_network.py:364-387); overrides ghost_ru.
+ * g_hist   optional [T][B][N][2]: dLoss/d(r, y) of the state BEFORE step t, i.e. a loss that reads the lane at every
+ *          step (what autograd through dmacro_lane.py:277-310 accumulates for such a loss).
+ * g_ghost  [B][2][2] summed over the steps, or with ghost_t: [T][B][2][2] per step. */
+int orc_arz_rollout_ex(const double *r0, const double *u0, const double *ghost_ru, const double *ghost_t,
+                       int B, int N, const double *dx, const double *umax, double dt, int T, int f32,
+                       double *rT, double *yT, double *uT,
+                       const double *g_rT, const double *g_yT, const double *g_uT, const double *g_hist,
+                       double *g_r0, double *g_u0, double *g_ghost, double *hist);
+
 int orc_arz_rollout(const double *r0, const double *u0, const double *ghost_ru,
                     int B, int N, const double *dx, const double *umax, double dt, int T, int f32,
                     double *rT, double *yT, double *uT,
                     const double *g_rT, const double *g_yT, const double *g_uT,
                     double *g_r0, double *g_u0, double *g_ghost, double *hist) {
+    return orc_arz_rollout_ex(r0, u0, ghost_ru, NULL, B, N, dx, umax, dt, T, f32, rT, yT, uT, g_rT, g_yT, g_uT, NULL,
+                              g_r0, g_u0, g_ghost, hist);
+}
+
+int orc_arz_rollout_ex(const double *r0, const double *u0, const double *ghost_ru, const double *ghost_t,
+                       int B, int N, const double *dx, const double *umax, double dt, int T, int f32,
+                       double *rT, double *yT, double *uT,
+                       const double *g_rT, const double *g_yT, const double *g_uT, const double *g_hist,
+                       double *g_r0, double *g_u0, double *g_ghost, double *hist) {
     int ncfl = 0;
     int P = N + 2;
 #pragma omp parallel for schedule(dynamic) reduction(+ : ncfl)
@@ -383,8 +403,9 @@ int orc_arz_rollout(const double *r0, const double *u0, const double *ghost_ru,
         int cfl = 0;
         for (int t = 0; t < T; t++) {
             pr = REC(t, 0); py = REC(t, 1); pu = REC(t, 2); pe = REC(t, 3);
+            const double *gh = ghost_t ? ghost_t + ((size_t)t * B + b) * 4 : ghost_ru + (size_t)b * 4;
             for (int s = 0; s < 2; s++) {
-                fullq_t q = from_r_u(ghost_ru[(size_t)b * 4 + s * 2], ghost_ru[(size_t)b * 4 + s * 2 + 1], um);
+                fullq_t q = from_r_u(gh[s * 2], gh[s * 2 + 1], um);
                 int i = s ? N + 1 : 0;
                 pr[i] = q.r; py[i] = rnd(q.y, f32); pu[i] = q.u; pe[i] = rnd(q.ueq, f32);
             }
@@ -421,14 +442,25 @@ int orc_arz_rollout(const double *r0, const double *u0, const double *ghost_ru,
             }
             for (int t = T - 1; t >= 0; t--) {
                 orc_arz_vjp(dq + (size_t)t * N * 12, N, gr, gy, f32, hr, hy);
+                const double *gh = ghost_t ? ghost_t + ((size_t)t * B + b) * 4 : ghost_ru + (size_t)b * 4;
                 for (int s = 0; s < 2; s++) {
                     int i = s ? N + 1 : 0;
                     double dyr, dyu;
-                    orc_dy_dru(ghost_ru[(size_t)b * 4 + s * 2], ghost_ru[(size_t)b * 4 + s * 2 + 1], um, &dyr, &dyu);
-                    gg[s * 2] += hr[i] + hy[i] * dyr;
-                    gg[s * 2 + 1] += hy[i] * dyu;
+                    orc_dy_dru(gh[s * 2], gh[s * 2 + 1], um, &dyr, &dyu);
+                    if (ghost_t && g_ghost) {
+                        g_ghost[((size_t)t * B + b) * 4 + s * 2] = hr[i] + hy[i] * dyr;
+                        g_ghost[((size_t)t * B + b) * 4 + s * 2 + 1] = hy[i] * dyu;
+                    } else {
+                        gg[s * 2] += hr[i] + hy[i] * dyr;
+                        gg[s * 2 + 1] += hy[i] * dyu;
+                    }
                 }
                 for (int j = 0; j < N; j++) { gr[j] = hr[j + 1]; gy[j] = hy[j + 1]; }
+                if (g_hist)
+                    for (int j = 0; j < N; j++) {
+                        gr[j] += g_hist[(((size_t)t * B + b) * N + j) * 2];
+                        gy[j] += g_hist[(((size_t)t * B + b) * N + j) * 2 + 1];
+                    }
             }
             for (int j = 0; j < N; j++) {
                 double dyr, dyu;
@@ -437,7 +469,7 @@ int orc_arz_rollout(const double *r0, const double *u0, const double *ghost_ru,
                 g_r0[(size_t)b * N + j] = gr[j] + gy[j] * dyr;
                 g_u0[(size_t)b * N + j] = gy[j] * dyu;
             }
-            if (g_ghost) for (int k = 0; k < 4; k++) g_ghost[(size_t)b * 4 + k] = gg[k];
+            if (g_ghost && !ghost_t) for (int k = 0; k < 4; k++) g_ghost[(size_t)b * 4 + k] = gg[k];
             free(gr);
         }
         #undef REC
@@ -544,14 +576,34 @@ void orc_idm_vjp(const double *dqs, int n, const double *g_np, const double *g_n
  * Outputs pT, vT [V]; adjoint (if g_pT): g_p0, g_v0 [V], g_head [L][2].
  * hist (optional) [T+1][V][2].  Returns total collisions.
  */
+/* head_t  optional [T][L][2]: head deltas PER STEP (inside a network RoadNetwork.setup_micro_boundary rewrites them before
+ *         every step, road_network.py:429-580); overrides head;  g_head is then [T][L][2], per step.
+ * g_hist  optional [T][V][2]: dLoss/d(p, v) of the state BEFORE step t (a loss that reads the lane at every step). */
+int orc_idm_rollout_ex(const double *p0, const double *v0, const double *params, int V, const int *lane_off, int L,
+                       const double *head, const double *head_t, double dt, int T, int f32, double *pT, double *vT,
+                       const double *g_pT, const double *g_vT, const double *g_hist, double *g_p0, double *g_v0,
+                       double *g_head, double *hist);
+
 int orc_idm_rollout(const double *p0, const double *v0, const double *params, int V, const int *lane_off, int L,
                     const double *head, double dt, int T, int f32, double *pT, double *vT, const double *g_pT,
                     const double *g_vT, double *g_p0, double *g_v0, double *g_head, double *hist) {
+    return orc_idm_rollout_ex(p0, v0, params, V, lane_off, L, head, NULL, dt, T, f32, pT, vT, g_pT, g_vT, NULL, g_p0, g_v0,
+                              g_head, hist);
+}
+
+int orc_idm_rollout_ex(const double *p0, const double *v0, const double *params, int V, const int *lane_off, int L,
+                       const double *head, const double *head_t, double dt, int T, int f32, double *pT, double *vT,
+                       const double *g_pT, const double *g_vT, const double *g_hist, double *g_p0, double *g_v0,
+                       double *g_head, double *hist) {
     int ncol = 0;
 #pragma omp parallel for schedule(dynamic) reduction(+ : ncol)
     for (int l = 0; l < L; l++) {
         int o = lane_off[l], n = lane_off[l + 1] - o;
-        if (n <= 0) { if (g_head) { g_head[2 * l] = 0; g_head[2 * l + 1] = 0; } continue; }
+        if (n <= 0) {
+            if (g_head && !head_t) { g_head[2 * l] = 0; g_head[2 * l + 1] = 0; }
+            for (int t = 0; g_head && head_t && t < T; t++) { g_head[((size_t)t * L + l) * 2] = 0; g_head[((size_t)t * L + l) * 2 + 1] = 0; }
+            continue;
+        }
         double *st = (double *)malloc(sizeof(double) * (size_t)(T + 1) * n * 2);
         double *dq = g_pT ? (double *)malloc(sizeof(double) * (size_t)T * n * 8) : NULL;
         double *par = (double *)malloc(sizeof(double) * 6 * n);
@@ -559,7 +611,8 @@ int orc_idm_rollout(const double *p0, const double *v0, const double *params, in
         for (int i = 0; i < n; i++) { st[i] = rnd(p0[o + i], f32); st[n + i] = rnd(v0[o + i], f32); }
         for (int t = 0; t < T; t++) {
             double *cp = st + (size_t)t * 2 * n, *cv = cp + n, *np_ = cp + 2 * n, *nv_ = np_ + n;
-            ncol += orc_idm_step(cp, cv, par, n, head[2 * l], head[2 * l + 1], dt, f32, np_, nv_, NULL,
+            const double *hd = head_t ? head_t + ((size_t)t * L + l) * 2 : head + 2 * l;
+            ncol += orc_idm_step(cp, cv, par, n, hd[0], hd[1], dt, f32, np_, nv_, NULL,
                                  dq ? dq + (size_t)t * n * 8 : NULL);
         }
         for (int t = 0; hist && t <= T; t++)
@@ -578,10 +631,19 @@ int orc_idm_rollout(const double *p0, const double *v0, const double *params, in
                 /* ghost = p_head + dp ; v_head - dv (dmicro_lane.py:144-151) */
                 hp[n - 1] += hp[n]; ghd += hp[n];
                 hv[n - 1] += hv[n]; ghv -= hv[n];
+                if (head_t && g_head) {
+                    g_head[((size_t)t * L + l) * 2] = ghd; g_head[((size_t)t * L + l) * 2 + 1] = ghv;
+                    ghd = 0; ghv = 0;
+                }
                 for (int i = 0; i < n; i++) { gp[i] = hp[i]; gv[i] = hv[i]; }
+                if (g_hist)
+                    for (int i = 0; i < n; i++) {
+                        gp[i] += g_hist[((size_t)t * V + o + i) * 2];
+                        gv[i] += g_hist[((size_t)t * V + o + i) * 2 + 1];
+                    }
             }
             for (int i = 0; i < n; i++) { g_p0[o + i] = gp[i]; g_v0[o + i] = gv[i]; }
-            if (g_head) { g_head[2 * l] = ghd; g_head[2 * l + 1] = ghv; }
+            if (g_head && !head_t) { g_head[2 * l] = ghd; g_head[2 * l + 1] = ghv; }
             free(gp);
         }
         free(st); free(par); if (dq) free(dq);

@@ -105,28 +105,35 @@ def arz_vjp(dqs, g_nr, g_ny, f32=False):
     return g_r, g_y
 
 
-def arz_rollout(r0, u0, ghost_ru, dx, umax, dt, T, f32=False, g_rT=None, g_yT=None, g_uT=None, want_hist=False):
-    """B lanes x N cells, static ghosts.  r0,u0 [B,N]; ghost_ru [B,2,2].
-    dx, umax scalars or [B].  Returns dict(rT,yT,uT,cfl[,g_r0,g_u0,g_ghost][,hist])."""
+def arz_rollout(r0, u0, ghost_ru, dx, umax, dt, T, f32=False, g_rT=None, g_yT=None, g_uT=None, want_hist=False, g_hist=None):
+    """B lanes x N cells.  r0,u0 [B,N]; ghost_ru [B,2,2] static ghosts or [T,B,2,2] one pair per step.
+    dx, umax scalars or [B].  g_hist [T,B,N,2]: dLoss/d(r,y) of the state before every step (per-step loss).
+    Returns dict(rT,yT,uT,cfl[,g_r0,g_u0,g_ghost][,hist]); g_ghost is [B,2,2] or, with per-step ghosts, [T,B,2,2]."""
     r0 = _d(r0); u0 = _d(u0); ghost_ru = _d(ghost_ru)
     B, N = r0.shape
+    tv = ghost_ru.ndim == 4
+    if tv:
+        assert ghost_ru.shape == (T, B, 2, 2)
     dx = _d(np.broadcast_to(np.asarray(dx, dtype=np.float64), (B,)))
     umax = _d(np.broadcast_to(np.asarray(umax, dtype=np.float64), (B,)))
     rT = np.zeros((B, N)); yT = np.zeros((B, N)); uT = np.zeros((B, N))
     hist = np.zeros((T + 1, B, N, 2)) if want_hist else None
-    bwd = g_rT is not None or g_uT is not None or g_yT is not None
+    bwd = g_rT is not None or g_uT is not None or g_yT is not None or g_hist is not None
     out = {}
     if bwd:
         g_rT = _d(g_rT) if g_rT is not None else np.zeros((B, N))
         g_yT = _d(g_yT) if g_yT is not None else np.zeros((B, N))
         g_uT = _d(g_uT) if g_uT is not None else np.zeros((B, N))
-        g_r0 = np.zeros((B, N)); g_u0 = np.zeros((B, N)); g_gh = np.zeros((B, 2, 2))
+        g_hist = _d(g_hist) if g_hist is not None else None
+        g_r0 = np.zeros((B, N)); g_u0 = np.zeros((B, N)); g_gh = np.zeros((T, B, 2, 2) if tv else (B, 2, 2))
     else:
         g_r0 = g_u0 = g_gh = None
-    cfl = lib().orc_arz_rollout(_p(r0), _p(u0), _p(ghost_ru), ctypes.c_int(B), ctypes.c_int(N), _p(dx), _p(umax),
-                                ctypes.c_double(dt), ctypes.c_int(T), ctypes.c_int(int(f32)), _p(rT), _p(yT), _p(uT),
-                                _p(g_rT) if bwd else None, _p(g_yT) if bwd else None, _p(g_uT) if bwd else None,
-                                _p(g_r0), _p(g_u0), _p(g_gh), _p(hist))
+    cfl = lib().orc_arz_rollout_ex(_p(r0), _p(u0),
+                                   _p(ghost_ru) if not tv else None, _p(ghost_ru) if tv else None,
+                                   ctypes.c_int(B), ctypes.c_int(N), _p(dx), _p(umax),
+                                   ctypes.c_double(dt), ctypes.c_int(T), ctypes.c_int(int(f32)), _p(rT), _p(yT), _p(uT),
+                                   _p(g_rT) if bwd else None, _p(g_yT) if bwd else None, _p(g_uT) if bwd else None,
+                                   _p(g_hist) if bwd else None, _p(g_r0), _p(g_u0), _p(g_gh), _p(hist))
     out.update(rT=rT, yT=yT, uT=uT, cfl=int(cfl))
     if bwd:
         out.update(g_r0=g_r0, g_u0=g_u0, g_ghost=g_gh)
@@ -156,23 +163,27 @@ def idm_vjp(dqs, g_np, g_ns, f32=False):
     return g_p, g_s
 
 
-def idm_rollout(p0, v0, params, lane_off, head, dt, T, f32=False, g_pT=None, g_vT=None, want_hist=False):
-    """CSR lanes.  p0,v0 [V]; params [6,V]; lane_off [L+1] int32; head [L,2]."""
+def idm_rollout(p0, v0, params, lane_off, head, dt, T, f32=False, g_pT=None, g_vT=None, want_hist=False, g_hist=None):
+    """CSR lanes.  p0,v0 [V]; params [6,V]; lane_off [L+1] int32; head [L,2] or, one pair per step, [T,L,2].
+    g_hist [T,V,2]: dLoss/d(p,v) of the state before every step.  g_head comes back [L,2] or [T,L,2]."""
     p0 = _d(p0); v0 = _d(v0); params = _d(params); head = _d(head)
     lane_off = np.ascontiguousarray(lane_off, dtype=np.int32)
     V = p0.shape[0]; L = lane_off.shape[0] - 1
+    tv = head.ndim == 3
     pT = np.zeros(V); vT = np.zeros(V)
     hist = np.zeros((T + 1, V, 2)) if want_hist else None
-    bwd = g_pT is not None
+    bwd = g_pT is not None or g_hist is not None
     if bwd:
-        g_pT = _d(g_pT); g_vT = _d(g_vT)
-        g_p0 = np.zeros(V); g_v0 = np.zeros(V); g_head = np.zeros((L, 2))
+        g_pT = _d(g_pT) if g_pT is not None else np.zeros(V); g_vT = _d(g_vT) if g_vT is not None else np.zeros(V)
+        g_hist = _d(g_hist) if g_hist is not None else None
+        g_p0 = np.zeros(V); g_v0 = np.zeros(V); g_head = np.zeros((T, L, 2) if tv else (L, 2))
     else:
         g_p0 = g_v0 = g_head = None
-    ncol = lib().orc_idm_rollout(_p(p0), _p(v0), _p(params), ctypes.c_int(V), _p(lane_off), ctypes.c_int(L), _p(head),
-                                 ctypes.c_double(dt), ctypes.c_int(T), ctypes.c_int(int(f32)), _p(pT), _p(vT),
-                                 _p(g_pT) if bwd else None, _p(g_vT) if bwd else None, _p(g_p0), _p(g_v0), _p(g_head),
-                                 _p(hist))
+    ncol = lib().orc_idm_rollout_ex(_p(p0), _p(v0), _p(params), ctypes.c_int(V), _p(lane_off), ctypes.c_int(L),
+                                    None if tv else _p(head), _p(head) if tv else None,
+                                    ctypes.c_double(dt), ctypes.c_int(T), ctypes.c_int(int(f32)), _p(pT), _p(vT),
+                                    _p(g_pT) if bwd else None, _p(g_vT) if bwd else None, _p(g_hist) if bwd else None,
+                                    _p(g_p0), _p(g_v0), _p(g_head), _p(hist))
     out = dict(pT=pT, vT=vT, ncol=int(ncol))
     if bwd:
         out.update(g_p0=g_p0, g_v0=g_v0, g_head=g_head)

@@ -310,3 +310,53 @@ def test_nan_gradient_flag_maps_to_assertion(dev, ckpt_every, N):
                 flags.check()
         else:
             flags.check()
+
+
+def test_rollout_per_step_coupling_vs_live_reference(dev):
+    """Per-step ghosts + a loss on the state before every step, against the live fp64 reference (arz_perstep_fp64.npz):
+    history, final state, gradients wrt the initial state and wrt every step's ghost cells."""
+    import dhts_b200
+    from dhts_b200 import functional as F
+    g = golden("arz_perstep_fp64")
+    T, umax = int(g["T"]), float(g["umax"])
+    flags = dhts_b200.Flags(dev)
+    r0 = T64(g["r0"], dev).requires_grad_(); u0 = T64(g["u0"], dev).requires_grad_()
+    gr = T64(g["ghost_ru"][..., 0], dev).requires_grad_(); gu = T64(g["ghost_ru"][..., 1], dev).requires_grad_()
+    rT, yT, uT, rh, yh = F.arz_rollout(r0, u0, gr, gu, float(g["dx"]), umax, float(g["dt"]), T, ckpt_every=1, flags=flags,
+                                       return_history=True)
+    uh = yh / rh.clamp(min=1e-5) + F.u_eq(rh.clamp(min=1e-5), umax)            # compute_u, model/macro/_arz.py:126-131
+    loss = (rh * T64(g["w_r"], dev)).sum() + (uh * T64(g["w_u"], dev)).sum() + (rT * T64(g["wT_r"], dev)).sum() \
+        + (uT * T64(g["wT_u"], dev)).sum()
+    loss.backward()
+    flags.check()
+    assert relerr(rh.detach().cpu(), g["r_hist"]) < 1e-9 and relerr(uh.detach().cpu(), g["u_hist"]) < 1e-9
+    assert relerr(rT.detach().cpu(), g["rT"]) < 1e-9 and relerr(uT.detach().cpu(), g["uT"]) < 1e-9
+    assert abs(float(loss) - float(g["loss"].sum())) < 1e-9 * abs(float(g["loss"].sum())) + 1e-9
+    assert relerr(r0.grad.cpu(), g["g_r0"]) < 1e-8 and relerr(u0.grad.cpu(), g["g_u0"]) < 1e-8
+    assert relerr(torch.stack([gr.grad, gu.grad], -1).cpu(), g["g_ghost"]) < 1e-8
+
+
+@pytest.mark.parametrize("B,N,T", [(5, 1024, 20), (37, 10, 40), (300, 33, 12)])
+def test_rollout_per_step_coupling_vs_oracle_shapes(dev, B, N, T):
+    """Same, on the bench's lane shape (4 cells per thread), many short lanes per CTA and ragged groups, vs the oracle."""
+    import dhts_b200
+    from dhts_b200 import functional as F
+    from oracle import oracle as O
+    rng = np.random.default_rng(B + N)
+    umax, dx, dt = 30.0, 5.0, 0.01
+    r0 = rng.uniform(0, 1, (B, N)); u0 = rng.uniform(0, 1, (B, N)) * umax
+    gh = np.stack([rng.uniform(0, 1, (T, B, 2)), rng.uniform(0, 1, (T, B, 2)) * umax], -1)
+    g_hist = rng.normal(size=(T, B, N, 2)) * np.array([1.0, 1.0 / umax])
+    wr = rng.normal(size=(B, N)); wu = rng.normal(size=(B, N)) / umax
+    flags = dhts_b200.Flags(dev)
+    tr = T64(r0, dev).requires_grad_(); tu = T64(u0, dev).requires_grad_()
+    tgr = T64(gh[..., 0], dev).requires_grad_(); tgu = T64(gh[..., 1], dev).requires_grad_()
+    rT, yT, uT, rh, yh = F.arz_rollout(tr, tu, tgr, tgu, dx, umax, dt, T, ckpt_every=1, flags=flags, return_history=True)
+    ((rh * T64(g_hist[..., 0], dev)).sum() + (yh * T64(g_hist[..., 1], dev)).sum() + (rT * T64(wr, dev)).sum()
+     + (uT * T64(wu, dev)).sum()).backward()
+    flags.check()
+    o = O.arz_rollout(r0, u0, gh, dx, umax, dt, T, g_rT=wr, g_uT=wu, g_hist=g_hist)
+    assert o["cfl"] == 0
+    assert relerr(rT.detach().cpu(), o["rT"]) < 1e-9 and relerr(uT.detach().cpu(), o["uT"]) < 1e-9
+    assert relerr(tr.grad.cpu(), o["g_r0"]) < 1e-8 and relerr(tu.grad.cpu(), o["g_u0"]) < 1e-8
+    assert relerr(torch.stack([tgr.grad, tgu.grad], -1).cpu(), o["g_ghost"]) < 1e-8

@@ -163,3 +163,34 @@ def test_rollout_nan_gradient_flag(dev, n, K):
         bits, _ = flags.read()
         assert bool(bits & FLAG_NAN_GRAD) == poison
         assert bool(torch.isnan(tp.grad[n:2 * n]).any()) == poison and not bool(torch.isnan(tp.grad[:n]).any())
+
+
+@pytest.mark.parametrize("L,n,T", [(6, 64, 40), (33, 10, 25), (4, 200, 12)])
+def test_rollout_per_step_coupling_vs_oracle(dev, L, n, T):
+    """Head deltas given PER STEP (what RoadNetwork.setup_micro_boundary does for a lane inside a network,
+    road_network.py:429-580) and a loss that reads the state before every step: final state, gradients wrt the
+    initial state and wrt every step's head deltas, against the oracle (pinned to the live reference by
+    tests/test_oracle_golden.py; its per-step extension is the composition of terminal-adjoint rollouts)."""
+    import dhts_b200
+    from dhts_b200 import functional as F
+    from oracle import oracle as O
+    rng = np.random.default_rng(L * 100 + n)
+    V, umax, dt = L * n, 30.0, 0.01
+    p0 = (np.arange(n)[None] * 16.0 + rng.uniform(0, 6, (L, n))).ravel(); v0 = rng.uniform(4, 22, V)
+    par = np.stack([rng.uniform(1.5, 2, V) * umax, rng.uniform(1, 1.5, V) * umax, rng.uniform(0.8, 1.2, V) * umax,
+                    rng.uniform(1, 2, V), rng.uniform(0.2, 0.6, V), np.full(V, 5.0)])
+    off = np.arange(L + 1) * n
+    head = np.stack([rng.uniform(15, 80, (T, L)), rng.uniform(-3, 3, (T, L))], -1)
+    g_hist = rng.normal(size=(T, V, 2)); wp = rng.normal(size=V); wv = rng.normal(size=V)
+    t = lambda a: torch.tensor(a, dtype=torch.float64, device=dev)
+    flags = dhts_b200.Flags(dev)
+    tp, tv, th_ = t(p0).requires_grad_(), t(v0).requires_grad_(), t(head).requires_grad_()
+    pT, vT, ph, vh = F.idm_rollout(tp, tv, t(par), torch.tensor(off, dtype=torch.int32, device=dev), th_, dt, T, ckpt_every=1,
+                                   flags=flags, return_history=True)
+    ((ph * t(g_hist[..., 0])).sum() + (vh * t(g_hist[..., 1])).sum() + (pT * t(wp)).sum() + (vT * t(wv)).sum()).backward()
+    flags.check(quiet_collisions=True)
+    o = O.idm_rollout(p0, v0, par, off, head, dt, T, g_pT=wp, g_vT=wv, g_hist=g_hist, want_hist=True)
+    assert relerr(pT.detach().cpu(), o["pT"]) < 1e-10 and relerr(vT.detach().cpu(), o["vT"]) < 1e-10
+    assert relerr(ph.detach().cpu(), o["hist"][:T, :, 0]) < 1e-10
+    assert relerr(tp.grad.cpu(), o["g_p0"]) < 1e-9 and relerr(tv.grad.cpu(), o["g_v0"]) < 1e-9
+    assert relerr(th_.grad.cpu(), o["g_head"]) < 1e-9

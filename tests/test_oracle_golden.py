@@ -88,3 +88,33 @@ def test_oracle_edge_cases():
     o = O.idm_rollout(np.zeros(0), np.zeros(0), np.zeros((6, 0)), [0, 0, 0], np.zeros((2, 2)), 0.01, 3,
                       g_pT=np.zeros(0), g_vT=np.zeros(0))
     assert o["pT"].shape == (0,)
+
+
+def test_arz_per_step_coupling_vs_live_reference():
+    """Per-step ghosts and a loss that reads the state before every step (oracle/gen_golden_perstep.py, live fp64 reference):
+    the oracle's g_hist injection and per-step ghost adjoints."""
+    from oracle import oracle as O
+    g = golden("arz_perstep_fp64")
+    T, B, N, umax = int(g["T"]), int(g["B"]), int(g["N"]), float(g["umax"])
+    f = O.arz_rollout(g["r0"], g["u0"], g["ghost_ru"], float(g["dx"]), umax, float(g["dt"]), T, want_hist=True)
+    hist = f["hist"]                                       # [T+1,B,N,2]
+    assert relerr(hist[:T, :, :, 0], g["r_hist"]) < 1e-12 and relerr(f["rT"], g["rT"]) < 1e-12 and relerr(f["uT"], g["uT"]) < 1e-12
+    # the loss reads (r, u) of the state before step t: chain u = compute_u(r, y) into (r, y) adjoints
+    g_hist = np.zeros((T, B, N, 2))
+    for t in range(T):
+        for b in range(B):
+            for j in range(N):
+                dr, dy = _du_dry(hist[t, b, j, 0], hist[t, b, j, 1], umax)
+                g_hist[t, b, j, 0] = g["w_r"][t, b, j] + g["w_u"][t, b, j] * dr
+                g_hist[t, b, j, 1] = g["w_u"][t, b, j] * dy
+    o = O.arz_rollout(g["r0"], g["u0"], g["ghost_ru"], float(g["dx"]), umax, float(g["dt"]), T, g_rT=g["wT_r"], g_uT=g["wT_u"],
+                      g_hist=g_hist)
+    assert relerr(o["g_r0"], g["g_r0"]) < 1e-10 and relerr(o["g_u0"], g["g_u0"]) < 1e-10
+    assert relerr(o["g_ghost"], g["g_ghost"]) < 1e-10
+
+
+def _du_dry(r, y, umax, eps=1e-5):
+    """d compute_u / d(r, y), the true derivative autograd takes outside the operator (model/macro/_arz.py:126-138)."""
+    if r >= eps:
+        return -y / (r * r) - 0.5 * umax / np.sqrt(r + eps), 1.0 / r
+    return 0.0, 1.0 / eps
