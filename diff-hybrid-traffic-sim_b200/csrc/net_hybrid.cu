@@ -48,12 +48,12 @@ namespace dhts {
 constexpr int FLAG_VEH_OVERFLOW = 16;
 constexpr int HYB_THREADS_MAX = 256;
 
-struct AuxL { int P, V, A, RID, CUR, FRONT, CNT, NSP, CAP, RMS, AUX; };
+struct AuxL { int P, V, A, RID, CUR, PID, FRONT, CNT, NSP, CAP, RMS, DRAW, AUX; };
 __host__ __device__ inline AuxL aux_layout(int ML, int cap, int NCAP) {
     AuxL o;
     const int s = ML * cap;
-    o.P = 0; o.V = s; o.A = 2 * s; o.RID = 3 * s; o.CUR = 4 * s; o.FRONT = 5 * s; o.CNT = o.FRONT + ML; o.NSP = o.CNT + ML;
-    o.CAP = o.NSP + ML; o.RMS = o.CAP + NCAP; o.AUX = o.RMS + 2;
+    o.P = 0; o.V = s; o.A = 2 * s; o.RID = 3 * s; o.CUR = 4 * s; o.PID = 5 * s; o.FRONT = 6 * s; o.CNT = o.FRONT + ML;
+    o.NSP = o.CNT + ML; o.CAP = o.NSP + ML; o.RMS = o.CAP + NCAP; o.DRAW = o.RMS + 2; o.AUX = o.DRAW + 1;
     return o;
 }
 
@@ -70,7 +70,13 @@ template <typename T> struct HybArgs {
     const T* lane_len;        // [L]
     const int* spawn_route;   // [Rs][ML][KS] route id of the k-th vehicle spawned into a micro lane
     long long spawn_stride;   // 0 when shared by all replicas
-    IdmPar<T> idm;            // parameters of every vehicle
+    const T* par_tab;         // [NP][6] IDM parameter sets (a_max, a_pref, v_target, s0, T, -); a vehicle names its set (PID), spawns use set 0
+    int NP;
+    T vlen;                   // length of every vehicle (RoadNetwork.vehicle_length, road_network.py:60)
+    const int* src;           // [ML] or null: 1 = boundary micro lane fed from a waiting list (_simulator.py:153-174)
+    const T* rnd;             // [Rr][NRAND] the uniform draws of the waiting-list source, in consumption order
+    long long rnd_stride;     // 0 when shared by all replicas
+    int NRAND;
     T head_dp0, head_dv0;     // DEFAULT_HEAD_POSITION_DELTA / DEFAULT_HEAD_SPEED_DELTA (_micro_lane.py:14-15)
     AuxL ax;
 };
@@ -109,7 +115,7 @@ __device__ __forceinline__ HeadRec<T> head_rec(const HybArgs<T>& a, int l, int m
     h.hs = f;
     h.ph = auxc[x.P + m * a.cap + f]; h.vh = auxc[x.V + m * a.cap + f];
     h.rid = (int)auxc[x.RID + m * a.cap + f]; h.cur = (int)auxc[x.CUR + m * a.cap + f];
-    const T len = a.lane_len[l], vlen = a.idm.len;
+    const T len = a.lane_len[l], vlen = a.vlen;
     // ---- leader along the route
     T acc = len - h.ph - vlen * T(0.5);
     h.gdp = a.head_dp0; h.gdv = a.head_dv0; h.lead_m = -1; h.lead_slot = 0; h.lead_clamped = false;
@@ -186,12 +192,22 @@ template <typename T> struct HybSm {
     int* walk;    // [NGL][6] lookups of the conversion walk of the current step (lane, kind, next / micro index, capacitor, ...)
     int* goff;    // [NG+1] group offsets (copy of grp_off)
     T* walkT;     // [NGL] length of the lane the walk asks about (macro: the micro successor; micro: the lane itself)
+    IdmPar<T>* par;  // [NP] parameter sets with their derived constants
+    int* srcf;    // [ML] waiting-list source: the lane had room at this step (one uniform draw consumed)
+    int* srcs;    // [ML] waiting-list source: ring slot of the vehicle that entered at this step, -1 = none
 };
 
 // Lanes sorted (stably) so that the threads of a warp do the same kind of work: macro lanes of equal length together,
 // micro lanes together.  Every thread calls it once per kernel; ends with a block barrier.
-template <typename T> __device__ __forceinline__ void hyb_lane_order(const HybArgs<T>& a, int* order) {
+template <typename T> __device__ __forceinline__ void hyb_lane_order(const HybArgs<T>& a, int* order, IdmPar<T>* par) {
     const NetArgs<T>& n = a.n;
+    for (int i = threadIdx.x; i < a.NP; i += blockDim.x) {      // parameter sets with the constants of _idm.py:31-40
+        const T* q = a.par_tab + (size_t)i * 6;
+        IdmPar<T> k;
+        k.a_max = q[0]; k.v_t_inv = T(1) / q[2]; k.s0 = q[3]; k.tp = q[4]; k.len = a.vlen;
+        k.sab2_inv = T(1) / (T(2) * t_sqrt(q[0] * q[1]));
+        par[i] = k;
+    }
     for (int l = threadIdx.x; l < n.L; l += blockDim.x) {
         const int key = n.kind[l] ? -1 : n.cell_off[l + 1] - n.cell_off[l];
         int rank = 0;
@@ -220,6 +236,52 @@ __device__ __forceinline__ void hyb_step(const HybArgs<T>& a, const HybSm<T>& s,
     const T* inc_t = n.incoming ? n.incoming + ((size_t)b * n.T_steps + t) * L : nullptr;
     const T inv_umax = T(1) / n.umax, inv15 = T(1) / (T(1.5) * n.umax), inv_dt = T(1) / n.dt;
     const bool blend = n.mode == 1 && n.soft && a.ML > 0;
+    const T vlen = a.vlen;
+    // ---- phase S: waiting-list sources (ItscpRoadNetwork.setup_micro_boundary, _simulator.py:153-174).  A boundary micro
+    // lane with room for a vehicle consumes ONE uniform draw -- lanes in id order within a step, so the draw a lane gets
+    // depends on how many lanes before it had room -- and, if the draw is below the scheduled inflow and its waiting list
+    // is not exhausted, receives a default vehicle at position 0 BEFORE the step (the row stored for step t does not hold
+    // it; the adjoint's replay re-inserts it).
+    if (a.src) {
+        T* auxw = s.aux[p];
+        for (int m = threadIdx.x; m < a.ML; m += blockDim.x) {
+            int room = 0;
+            if (a.src[m]) {
+                const int cnt = (int)auxw[x.CNT + m];
+                const T space = cnt > 0 ? auxw[x.P + m * a.cap + ((int)auxw[x.FRONT + m] + cnt - 1) % a.cap] - vlen * T(0.5)
+                                        : a.lane_len[a.mic_lane[m]];                  // entering_free_space, _micro_lane.py:289-301
+                room = space > vlen * T(0.5);
+            }
+            s.srcf[m] = room;
+        }
+        __syncthreads();
+        for (int m = threadIdx.x; m < a.ML; m += blockDim.x) {
+            int slot = -1;
+            if (s.srcf[m]) {
+                int idx = (int)auxw[x.DRAW];
+                for (int q = 0; q < m; q++) idx += s.srcf[q];
+                if (idx >= a.NRAND) fl |= FLAG_VEH_OVERFLOW;
+                else {
+                    const T u = a.rnd[(size_t)b * a.rnd_stride + idx];
+                    const int ord = (int)auxw[x.NSP + m];
+                    if (u < inc_t[a.mic_lane[m]] && ord < a.KS) {                     // the list still holds a vehicle and a route
+                        const int f = (int)auxw[x.FRONT + m], cnt = (int)auxw[x.CNT + m];
+                        if (cnt >= a.cap) fl |= FLAG_VEH_OVERFLOW;
+                        else {
+                            slot = (f + cnt) % a.cap;
+                            const int o = m * a.cap + slot;
+                            auxw[x.P + o] = T(0); auxw[x.V + o] = T(0); auxw[x.A + o] = vlen;       // default_micro_vehicle, micro_vehicle.py:30-72
+                            auxw[x.RID + o] = (T)a.spawn_route[(size_t)b * a.spawn_stride + (size_t)m * a.KS + ord];
+                            auxw[x.CUR + o] = T(0); auxw[x.PID + o] = T(0);
+                            auxw[x.CNT + m] = (T)(cnt + 1); auxw[x.NSP + m] = (T)(ord + 1);
+                        }
+                    }
+                }
+            }
+            s.srcs[m] = slot;
+        }
+        __syncthreads();
+    }
     // ---- phase 0: final_signal of every head vehicle (the running mean visits the micro lanes in id order)
     if (blend) {
         for (int m = threadIdx.x; m < a.ML; m += blockDim.x) {
@@ -266,7 +328,7 @@ __device__ __forceinline__ void hyb_step(const HybArgs<T>& a, const HybSm<T>& s,
             for (int q = 0; q < a.cap; q++) {
                 const int o = m * a.cap + q;
                 auxn[x.P + o] = auxc[x.P + o]; auxn[x.V + o] = auxc[x.V + o]; auxn[x.A + o] = auxc[x.A + o];
-                auxn[x.RID + o] = auxc[x.RID + o]; auxn[x.CUR + o] = auxc[x.CUR + o];
+                auxn[x.RID + o] = auxc[x.RID + o]; auxn[x.CUR + o] = auxc[x.CUR + o]; auxn[x.PID + o] = auxc[x.PID + o];
             }
             T dp = a.head_dp0, dv = a.head_dv0, kc = T(0);
             if (cnt > 0) {
@@ -288,9 +350,9 @@ __device__ __forceinline__ void hyb_step(const HybArgs<T>& a, const HybSm<T>& s,
                 for (int j = 0; j < cnt; j++) {
                     const int o = m * a.cap + (f + j) % a.cap;
                     const T pj = auxc[x.P + o], vj = auxc[x.V + o];
-                    const T dpr = j == 0 ? dp : t_abs(pl - pj) - a.idm.len;        // (len + len) / 2
+                    const T dpr = j == 0 ? dp : t_abs(pl - pj) - vlen;             // (len + len) / 2
                     const T dvr = j == 0 ? dv : vj - vl;
-                    const IdmEval<T> e = idm_eval(vj, a.idm, dpr, dvr, inv_dt);
+                    const IdmEval<T> e = idm_eval(vj, s.par[(int)auxc[x.PID + o]], dpr, dvr, inv_dt);
                     if (e.col) ncol++;
                     auxn[x.P + o] = pj + n.dt * vj; auxn[x.V + o] = vj + n.dt * e.acc;
                     pl = pj; vl = vj;
@@ -301,6 +363,9 @@ __device__ __forceinline__ void hyb_step(const HybArgs<T>& a, const HybSm<T>& s,
                 T sum = auxc[x.RMS], num = auxc[x.RMS + 1];
                 if (blend) for (int q = 0; q < a.ML; q++) { sum += s.fsig[2 * q] * s.fsig[2 * q + 1]; num += s.fsig[2 * q + 1]; }
                 auxn[x.RMS] = sum; auxn[x.RMS + 1] = num;
+                T nd = auxc[x.DRAW];
+                if (a.src) for (int q = 0; q < a.ML; q++) nd += (T)s.srcf[q];
+                auxn[x.DRAW] = nd;
             }
         }
     }
@@ -333,7 +398,6 @@ __device__ __forceinline__ void hyb_step(const HybArgs<T>& a, const HybSm<T>& s,
         __syncthreads();
     }
     // ---- phase 2: conversions, one thread per group, lanes in id order (road_network.py:113-173)
-    const T vlen = a.idm.len;
     for (int g = threadIdx.x; g < a.NG; g += blockDim.x) {
         for (int gi = s.goff[g]; gi < s.goff[g + 1]; gi++) {
             const int* w = s.walk + gi * 6;
@@ -359,7 +423,7 @@ __device__ __forceinline__ void hyb_step(const HybArgs<T>& a, const HybSm<T>& s,
                                 const int sl_ = (f2 + n2) % a.cap, o = m2 * a.cap + sl_;
                                 auxn[x.P + o] = T(0); auxn[x.V + o] = ul; auxn[x.A + o] = flux - (flux - vlen);
                                 auxn[x.RID + o] = (T)a.spawn_route[(size_t)b * a.spawn_stride + (size_t)m2 * a.KS + ord];
-                                auxn[x.CUR + o] = T(0);
+                                auxn[x.CUR + o] = T(0); auxn[x.PID + o] = T(0);
                                 auxn[x.CNT + m2] = (T)(n2 + 1); auxn[x.NSP + m2] = (T)(ord + 1);
                                 auxn[x.CAP + k] = flux - vlen;                    // re-created detached, :65-68
                                 ev = EV_SPAWN; e1 = m2; e3 = sl_;
@@ -374,6 +438,7 @@ __device__ __forceinline__ void hyb_step(const HybArgs<T>& a, const HybSm<T>& s,
                     const int o = m * a.cap + f;
                     const T ph = auxn[x.P + o], vh = auxn[x.V + o], ah = auxn[x.A + o];
                     const int rid = (int)auxn[x.RID + o], cur = (int)auxn[x.CUR + o];
+                    const T pid = auxn[x.PID + o];
                     const int nx = route_at(a, rid, cur + 1);
                     const T len = s.walkT[gi];
                     bool pop = false;
@@ -407,7 +472,7 @@ __device__ __forceinline__ void hyb_step(const HybArgs<T>& a, const HybSm<T>& s,
                             else {
                                 const int s2 = (f2 + n2) % a.cap, o2 = m2 * a.cap + s2;
                                 auxn[x.P + o2] = ph - len; auxn[x.V + o2] = vh; auxn[x.A + o2] = ah;
-                                auxn[x.RID + o2] = (T)rid; auxn[x.CUR + o2] = (T)(cur + 1);
+                                auxn[x.RID + o2] = (T)rid; auxn[x.CUR + o2] = (T)(cur + 1); auxn[x.PID + o2] = pid;
                                 auxn[x.CNT + m2] = (T)(n2 + 1);
                                 ev = EV_MOVE; e2 = m2; e3 = s2;
                             }
@@ -443,6 +508,9 @@ template <typename T> __device__ __forceinline__ HybSm<T> hyb_carve(const HybArg
     s.walk = reinterpret_cast<int*>(q); q += ((size_t)a.NGL * 6 * sizeof(int) + sizeof(T) - 1) / sizeof(T);
     s.goff = reinterpret_cast<int*>(q); q += ((size_t)(a.NG + 1) * sizeof(int) + sizeof(T) - 1) / sizeof(T);
     s.walkT = q; q += a.NGL;
+    s.par = reinterpret_cast<IdmPar<T>*>(q); q += ((size_t)a.NP * sizeof(IdmPar<T>) + sizeof(T) - 1) / sizeof(T);
+    s.srcf = reinterpret_cast<int*>(q); q += ((size_t)2 * a.ML * sizeof(int) + sizeof(T) - 1) / sizeof(T);
+    s.srcs = s.srcf + a.ML;
     extra = q;
     return s;
 }
@@ -460,7 +528,7 @@ __global__ void __launch_bounds__(HYB_THREADS_MAX) hyb_rollout_fwd_kernel(HybArg
     extern __shared__ __align__(16) unsigned char raw[];
     T* extra;
     const HybSm<T> s = hyb_carve(a, raw, false, extra);
-    hyb_lane_order(a, s.order);
+    hyb_lane_order(a, s.order, s.par);
     const int NC = a.n.NC, AUX = a.ax.AUX, n_own = a.n.n_own;
     unsigned fl = 0; int ncol = 0;
     for (int b = blockIdx.x; b < a.n.R; b += gridDim.x) {
@@ -473,7 +541,7 @@ __global__ void __launch_bounds__(HYB_THREADS_MAX) hyb_rollout_fwd_kernel(HybArg
             s.st[0][3 * NC + c] = ueq0 ? ueq0[(size_t)b * NC + c] : u_eq(r, a.n.umax);
         }
         for (int c = threadIdx.x; c < 2 * n_own; c += blockDim.x) s.own[0][c] = own0[(size_t)b * 2 * n_own + c];
-        for (int c = threadIdx.x; c < AUX; c += blockDim.x) s.aux[0][c] = aux0[(size_t)b * AUX + c];
+        for (int c = threadIdx.x; c < AUX; c += blockDim.x) { s.aux[0][c] = aux0[(size_t)b * AUX + c]; s.aux[1][c] = T(0); }
         __syncthreads();
         int p = 0;
         for (int t = 0; t <= a.n.T_steps; t++) {
@@ -517,7 +585,7 @@ __global__ void __launch_bounds__(TMAX, TMAX <= 192 ? 2 : 1) hyb_rollout_bwd_ker
     extern __shared__ __align__(16) unsigned char raw[];
     T* q;
     HybSm<T> s = hyb_carve(a, raw, true, q);
-    hyb_lane_order(a, s.order);
+    hyb_lane_order(a, s.order, s.par);
     const NetArgs<T>& n = a.n;
     const AuxL& x = a.ax;
     const int NC = n.NC, L = n.L, AUX = x.AUX, n_own = n.n_own, ML = a.ML, cap = a.cap;
@@ -535,7 +603,7 @@ __global__ void __launch_bounds__(TMAX, TMAX <= 192 ? 2 : 1) hyb_rollout_bwd_ker
     int* pubi = reinterpret_cast<int*>(q);     // [ML][4] prev lane, next lane, leader micro index, leader slot
     s.log.ei = pubi + 4 * ML;                  // [NGL][4]
     const T inv_umax = T(1) / n.umax, inv15 = T(1) / (T(1.5) * n.umax), inv_dt = T(1) / n.dt;
-    const T vlen = a.idm.len;
+    const T vlen = a.vlen;
     bool nan = false;
     unsigned fl = 0; int ncol = 0;
     for (int b = blockIdx.x; b < n.R; b += gridDim.x) {
@@ -704,9 +772,10 @@ __global__ void __launch_bounds__(TMAX, TMAX <= 192 ? 2 : 1) hyb_rollout_bwd_ker
                             const T pj = auxc[x.P + o], vj = auxc[x.V + o];
                             const T dpr = j == 0 ? dp : t_abs(pl - pj) - vlen;
                             const T dvr = j == 0 ? dv : vj - vl;
-                            const IdmEval<T> e = idm_eval(vj, a.idm, dpr, dvr, inv_dt);
+                            const IdmPar<T>& ip = s.par[(int)auxc[x.PID + o]];
+                            const IdmEval<T> e = idm_eval(vj, ip, dpr, dvr, inv_dt);
                             T E10, E11, L10, L11;
-                            idm_jac(vj, a.idm, dpr, dvr, e, n.dt, E10, E11, L10, L11);
+                            idm_jac(vj, ip, dpr, dvr, e, n.dt, E10, E11, L10, L11);
                             const T gp = GV[o], gv = GV[ML * cap + o];
                             T op = gp + E10 * gv, ov = n.dt * gp + E11 * gv;
                             const T sp = L10 * gv, sv = L11 * gv;
@@ -793,6 +862,10 @@ __global__ void __launch_bounds__(TMAX, TMAX <= 192 ? 2 : 1) hyb_rollout_bwd_ker
                             for (int k = 0; k < 3; k++) GV[k * ML * cap + o] += ga[k * ML * cap + o];
                         }
                     }
+                    if (a.src && s.srcs[m] >= 0) {      // the vehicle that entered from the waiting list at step t: a constant
+                        const int o = m * cap + s.srcs[m];
+                        GV[o] = T(0); GV[ML * cap + o] = T(0); GV[2 * ML * cap + o] = T(0);
+                    }
                 }
                 if (g_sig) g_sig[((size_t)b * n.T_steps + t) * L + l] = gsig;
                 nan |= t_isnan(gsig);
@@ -843,6 +916,8 @@ template <typename T> static size_t hyb_smem(const HybArgs<T>& a, bool adj) {
     bytes += sizeof(int) * L + sizeof(T);                                  // order
     bytes += sizeof(int) * 6 * (size_t)a.NGL + sizeof(T);                  // walk
     bytes += sizeof(int) * (size_t)(a.NG + 1) + sizeof(T); el += a.NGL;   // goff, walkT
+    bytes += sizeof(IdmPar<T>) * (size_t)a.NP + sizeof(T);                // par
+    bytes += sizeof(int) * 2 * ML + sizeof(T);                            // srcf, srcs
     return sizeof(T) * el + bytes + 32;
 }
 
@@ -855,6 +930,8 @@ template <typename T> static int hyb_check(const HybArgs<T>& a) {
     if (a.ML > 0 && (!a.mic_lane || !a.routes || (a.NCAP > 0 && (!a.cap_lane || !a.spawn_route || !n.route)))) return DHTS_ERR_INVALID;
     if (n.mode == 1 && (!n.sig || !n.incoming)) return DHTS_ERR_INVALID;
     if (n.mode != 0 && n.mode != 1) return DHTS_ERR_INVALID;
+    if (a.NP < 1 || !a.par_tab || !(a.vlen > T(0))) return DHTS_ERR_INVALID;
+    if (a.src && (n.mode != 1 || !a.rnd || a.NRAND < 0 || (a.KS > 0 && !a.spawn_route))) return DHTS_ERR_INVALID;
     return DHTS_OK;
 }
 
@@ -875,22 +952,22 @@ template <typename K> static int hyb_launch_cfg(K kernel, size_t smem, int threa
 template <typename T>
 static HybArgs<T> hyb_args(const dhts_hyb_topology* tp, const T* dx, const T* lane_len, const int* route, int route_per_replica,
                            const int* spawn_route, int spawn_per_replica, int KS, const T* sig, const T* incoming,
-                           const T* veh_par, T umax, T dt, int steps, int R, int mode, int soft) {
+                           const T* veh_par, int n_par, T veh_len, const T* src_rand, int n_rand, int rand_per_replica,
+                           T umax, T dt, int steps, int R, int mode, int soft) {
     HybArgs<T> a;
     NetArgs<T>& n = a.n;
     n.L = tp->L; n.NC = tp->NC; n.n_own = tp->n_own; n.T_steps = steps; n.R = R; n.mode = mode; n.soft = soft;
     n.cell_off = tp->cell_off; n.dx = dx; n.nadj = tp->nadj; n.one_adj = tp->one_adj; n.adj_off = tp->adj_off; n.adj = tp->adj;
     n.own_slot = tp->own_slot; n.route = route; n.route_stride = route_per_replica ? (long long)steps * 2 * tp->L : 0;
-    n.umax = umax; n.dt = dt; n.veh_len = veh_par[5]; n.static_speed = T(0);
+    n.umax = umax; n.dt = dt; n.veh_len = veh_len; n.static_speed = T(0);
     n.sig = sig; n.incoming = incoming; n.qk = nullptr; n.kind = tp->kind;
     a.ML = tp->ML; a.cap = tp->cap; a.NCAP = tp->NCAP; a.NGL = tp->NGL; a.NG = tp->NG; a.RLEN = tp->RLEN; a.NR = tp->NR;
     a.KS = KS; a.MAXT = tp->MAXT;
     a.mic_of = tp->mic_of; a.mic_lane = tp->mic_lane; a.cap_off = tp->cap_off; a.cap_lane = tp->cap_lane;
     a.grp_off = tp->grp_off; a.grp_lane = tp->grp_lane; a.routes = tp->routes; a.lane_len = lane_len;
     a.spawn_route = spawn_route; a.spawn_stride = spawn_per_replica ? (long long)tp->ML * KS : 0;
-    // (a_max, a_pref, v_target, s0, T, length) as in the IDM lane kernels' params rows
-    a.idm.a_max = veh_par[0]; a.idm.v_t_inv = T(1) / veh_par[2]; a.idm.s0 = veh_par[3]; a.idm.tp = veh_par[4];
-    a.idm.len = veh_par[5]; a.idm.sab2_inv = T(1) / (T(2) * std::sqrt(veh_par[0] * veh_par[1]));
+    a.par_tab = veh_par; a.NP = n_par; a.vlen = veh_len;
+    a.src = tp->src; a.rnd = src_rand; a.NRAND = n_rand; a.rnd_stride = rand_per_replica ? (long long)n_rand : 0;
     a.head_dp0 = T(1000); a.head_dv0 = T(0);
     a.ax = aux_layout(tp->ML, tp->cap, tp->NCAP);
     return a;
@@ -902,14 +979,17 @@ static HybArgs<T> hyb_args(const dhts_hyb_topology* tp, const T* dx, const T* la
     DHTS_EXPORT int dhts_hyb_rollout_fwd_##SUF(const dhts_hyb_topology* topo, const T* dx, const T* lane_len,          \
                                                const int* route, int route_per_replica, const int* spawn_route,        \
                                                int spawn_per_replica, int KS, const T* sig, const T* incoming,         \
-                                               const T* veh_par, T umax, T dt, int steps, int R, int mode, int soft,   \
+                                               const T* veh_par, int n_par, T veh_len, const T* src_rand, int n_rand,  \
+                                               int rand_per_replica, T umax, T dt, int steps, int R, int mode,         \
+                                               int soft,                                                               \
                                                const T* r0, const T* y0, const T* u0, const T* ueq0, const T* own0,    \
                                                const T* aux0, T* hist, T* own_hist, T* aux_hist, T* head_hist,         \
                                                int* flags, void* stream) {                                             \
-        if (!topo || !veh_par || !r0 || !y0 || !u0 || !aux0 || !hist || !aux_hist || !flags) return DHTS_ERR_INVALID;  \
+        if (!topo || !veh_par || !aux0 || !aux_hist || !flags) return DHTS_ERR_INVALID;                                \
+        if (topo->NC > 0 && (!r0 || !y0 || !u0 || !hist)) return DHTS_ERR_INVALID;                                     \
         dhts::HybArgs<T> a = dhts::hyb_args<T>(topo, dx, lane_len, route, route_per_replica, spawn_route,              \
-                                               spawn_per_replica, KS, sig, incoming, veh_par, umax, dt, steps, R,      \
-                                               mode, soft);                                                            \
+                                               spawn_per_replica, KS, sig, incoming, veh_par, n_par, veh_len,          \
+                                               src_rand, n_rand, rand_per_replica, umax, dt, steps, R, mode, soft);   \
         int rc = dhts::hyb_check(a);                                                                                   \
         if (rc) return rc;                                                                                             \
         if (a.n.n_own > 0 && (!own0 || !own_hist)) return DHTS_ERR_INVALID;                                            \
@@ -927,15 +1007,18 @@ static HybArgs<T> hyb_args(const dhts_hyb_topology* tp, const T* dx, const T* la
     DHTS_EXPORT int dhts_hyb_rollout_bwd_##SUF(const dhts_hyb_topology* topo, const T* dx, const T* lane_len,          \
                                                const int* route, int route_per_replica, const int* spawn_route,        \
                                                int spawn_per_replica, int KS, const T* sig, const T* incoming,         \
-                                               const T* veh_par, T umax, T dt, int steps, int R, int mode, int soft,   \
+                                               const T* veh_par, int n_par, T veh_len, const T* src_rand, int n_rand,  \
+                                               int rand_per_replica, T umax, T dt, int steps, int R, int mode,         \
+                                               int soft,                                                               \
                                                const T* hist, const T* own_hist, const T* aux_hist,                    \
                                                const T* g_states, const T* g_aux, T* g_r0, T* g_y0, T* g_u0,           \
                                                T* g_own0, T* g_sig, T* g_incoming, T* g_aux0, int* flags,              \
                                                void* stream) {                                                         \
-        if (!topo || !veh_par || !hist || !aux_hist || !g_r0 || !g_y0 || !g_u0 || !flags) return DHTS_ERR_INVALID;     \
+        if (!topo || !veh_par || !aux_hist || !flags) return DHTS_ERR_INVALID;                                         \
+        if (topo->NC > 0 && (!hist || !g_r0 || !g_y0 || !g_u0)) return DHTS_ERR_INVALID;                               \
         dhts::HybArgs<T> a = dhts::hyb_args<T>(topo, dx, lane_len, route, route_per_replica, spawn_route,              \
-                                               spawn_per_replica, KS, sig, incoming, veh_par, umax, dt, steps, R,      \
-                                               mode, soft);                                                            \
+                                               spawn_per_replica, KS, sig, incoming, veh_par, n_par, veh_len,          \
+                                               src_rand, n_rand, rand_per_replica, umax, dt, steps, R, mode, soft);   \
         int rc = dhts::hyb_check(a);                                                                                   \
         if (rc) return rc;                                                                                             \
         if (a.n.n_own > 0 && !own_hist) return DHTS_ERR_INVALID;                                                       \

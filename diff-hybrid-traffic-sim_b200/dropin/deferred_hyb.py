@@ -70,16 +70,19 @@ def flush_hyb(net, steps, dt, diff, replay):
     L, cap, ML = topo.L, topo.veh_cap, topo.ML
     umax = float(net.speed_limit)
     par = default_vehicle_params(umax, float(net.vehicle_length))
-    # ---- vehicles present: default parameters, routes the topology knows, head first per micro lane
+    # ---- vehicles present: their own IDM parameter sets (set 0 = what spawned vehicles get), routes the topology knows,
+    # head first per micro lane
     p0 = torch.zeros((1, max(ML, 1), cap), dtype=sd, device=dev); v0 = torch.zeros_like(p0); a0 = torch.zeros_like(p0)
-    route0 = np.zeros((max(ML, 1), cap)); count0 = np.zeros(max(ML, 1))
+    route0 = np.zeros((max(ML, 1), cap)); count0 = np.zeros(max(ML, 1)); pid0 = np.zeros((max(ML, 1), cap))
+    par_sets = [tuple(float(x) for x in par)]
+    par_idx = {par_sets[0]: 0}
     olds = []
     for m, l in enumerate(topo.micro):
         veh = lanes[l]._curr_vehicle
         if len(veh) > cap - 2:
             return replay()
         for mv in veh:
-            if [float(x) for x in mv.idm_params()] != [float(x) for x in par] or mv.id not in net._micro_route:
+            if float(mv.idm_params()[5]) != par_sets[0][5] or mv.id not in net._micro_route:
                 return replay()
         olds.append(list(reversed(veh)))
         if veh:
@@ -89,6 +92,10 @@ def flush_hyb(net, steps, dt, diff, replay):
             a0[0, m, :n] = rt.gather([mv.a for mv in olds[-1]], sd)
             count0[m] = n
             for k, mv in enumerate(olds[-1]):
+                key = tuple(float(x) for x in mv.idm_params())
+                if key not in par_idx:
+                    par_idx[key] = len(par_sets); par_sets.append(key)
+                pid0[m, k] = par_idx[key]
                 mr = net._micro_route[mv.id]
                 try:
                     route0[m, k] = topo.route_id(mr.route[mr.curr_idx:])
@@ -107,7 +114,8 @@ def flush_hyb(net, steps, dt, diff, replay):
     own0 = torch.stack(own).to(sd).reshape(1, topo.n_own, 2) if own else None
     cap_pairs = [(l, topo.cap_lane[j]) for l in range(L) for j in range(topo.cap_off[l], topo.cap_off[l + 1])]
     capac = rt.gather([lanes[a]._flux_capacitor.get(b, 0.0) for a, b in cap_pairs], sd).reshape(1, -1) if cap_pairs else None
-    aux0 = topo.make_aux0(1, sd, p0[:, :ML], v0[:, :ML], a0[:, :ML], route0[:ML], count0[:ML], capac)
+    aux0 = topo.make_aux0(1, sd, p0[:, :ML], v0[:, :ML], a0[:, :ML], route0[:ML], count0[:ML], capac, pid0=pid0[:ML])
+    par = [list(k) for k in par_sets]
     mroute = net._macro_route
     row = torch.tensor([[[mroute.get_prev_lane(l) for l in range(L)], [mroute.get_next_lane(l) for l in range(L)]]],
                        dtype=torch.int32, device=dev)

@@ -13,10 +13,19 @@ spawned into micro lane m; ``HybridNetTopology.random_spawn_routes`` draws them 
 every hop).  Only the part of a route up to its first macro lane matters (the vehicle is absorbed there), so routes
 are stored as "micro prefix + first macro lane".
 
-Restrictions: on a cycle of micro lanes a vehicle route ends where every successor has been visited (``cyclic_micro``;
-the reference would let it circulate for up to 32 hops); checked: every spawned vehicle has ``default_micro_vehicle`` parameters (one parameter set per
-call); in ITSCP mode every micro lane has a predecessor (the stochastic waiting-list source of
-_simulator.py:153-174 is host-side and not fused).
+IDM parameters are per VEHICLE: a call takes a table of parameter sets (``veh_params`` [NP, 6]) and every initial vehicle
+names its set (``make_aux0(pid0=...)``; MicroVehicle's own attributes, road/vehicle/micro_vehicle.py:74-122); vehicles the
+network creates itself (macro->micro spawns, waiting-list entries) are ``default_micro_vehicle``s = set 0, as in the
+reference (conversion.py:53-57, _env.py:202-219).
+
+ITSCP MICRO mode (every lane a plain ``MicroLane``, _env.py:484-488): ``sources=True`` marks the micro lanes without
+predecessor as fed from a waiting list (_simulator.py:153-174).  The uniform draws the reference takes from
+``np.random`` while a lane has room are an INPUT (``src_rand``, consumption order), like the waiting routes
+(``spawn_route`` rows in pop order).
+
+Restriction: with ``enumerate_routes=True`` (default) a vehicle route on a cycle of micro lanes ends where every
+successor has been visited (``cyclic_micro``; the reference would let it circulate for up to 32 hops);
+``enumerate_routes=False`` registers routes as they are named (``route_id``) and takes them as they are.
 """
 from __future__ import annotations
 
@@ -43,7 +52,7 @@ class _HybTopoStruct(ctypes.Structure):
                 ("NGL", ctypes.c_int), ("NR", ctypes.c_int), ("RLEN", ctypes.c_int), ("MAXT", ctypes.c_int),
                 ("kind", ctypes.c_void_p), ("mic_of", ctypes.c_void_p), ("mic_lane", ctypes.c_void_p),
                 ("cap_off", ctypes.c_void_p), ("cap_lane", ctypes.c_void_p), ("grp_off", ctypes.c_void_p),
-                ("grp_lane", ctypes.c_void_p), ("routes", ctypes.c_void_p)]
+                ("grp_lane", ctypes.c_void_p), ("routes", ctypes.c_void_p), ("src", ctypes.c_void_p)]
 
 
 def default_vehicle_params(speed_limit: float, length: float = 5.0) -> List[float]:
@@ -57,7 +66,8 @@ class HybridNetTopology:
 
     def __init__(self, kind: Sequence[int], num_cell: Sequence[int], cell_length: Sequence[float],
                  lane_length: Sequence[float], links: Sequence[Tuple[int, int]], device, mode: int = MODE_PLAIN,
-                 veh_cap: int = 8, veh_len: float = 5.0, max_routes: int = 4096):
+                 veh_cap: int = 8, veh_len: float = 5.0, max_routes: int = 4096, sources: bool = False,
+                 enumerate_routes: bool = True):
         L = len(kind)
         assert L >= 1 and len(num_cell) == L == len(cell_length) == len(lane_length)
         self.L, self.mode = L, int(mode)
@@ -88,8 +98,11 @@ class HybridNetTopology:
         for i, l in enumerate(self.micro):
             mic_of[l] = i
         self.mic_of = mic_of
-        if self.mode == MODE_ITSCP:
-            assert all(prev[l] for l in self.micro), "ITSCP mode: micro lanes without predecessor spawn from a host-side waiting list"
+        self.sources = bool(sources)
+        if self.mode == MODE_ITSCP and not self.sources:
+            assert all(prev[l] for l in self.micro), "ITSCP mode: micro lanes without predecessor are waiting-list sources (sources=True)"
+        assert not self.sources or self.mode == MODE_ITSCP, "waiting-list sources belong to the ITSCP simulator"
+        self.src = [int(self.sources and not prev[l]) for l in self.micro]
         nadj = [len(p) for p in prev] + [len(n) for n in nxt]
         one = [p[0] if len(p) == 1 else -1 for p in prev] + [n[0] if len(n) == 1 else -1 for n in nxt]
         adj, adj_off = [], []
@@ -169,8 +182,10 @@ class HybridNetTopology:
             if all(x in path for x in nxt[l]):
                 self.route_index[tuple(path)] = len(self.routes); self.routes.append(tuple(path))
 
-        for l in self.micro:
-            walk([l])
+        self.enumerate_routes = bool(enumerate_routes)
+        if self.enumerate_routes:
+            for l in self.micro:
+                walk([l])
         route_rows = [list(r) + [-1] * (ROUTE_LEN - len(r)) for r in self.routes] or [[-1] * ROUTE_LEN]
         dxs = [self.cell_length[l] for l in range(L) if not self.kind[l]]
         self.MAXT = int(math.ceil(self.veh_len / min(dxs))) + 1 if dxs else 1
@@ -178,7 +193,7 @@ class HybridNetTopology:
         parts = {"cell_off": cell_off, "nadj": nadj, "one_adj": one, "adj_off": adj_off, "adj": adj or [0], "own_slot": own_slot,
                  "kind": self.kind, "mic_of": mic_of, "mic_lane": self.micro or [0], "cap_off": cap_off,
                  "cap_lane": cap_lane or [0], "grp_off": grp_off, "grp_lane": grp_lane or [0],
-                 "routes": [x for row in route_rows for x in row]}
+                 "routes": [x for row in route_rows for x in row], "src": self.src or [0]}
         self.host = parts
         self._dev: Dict[str, torch.Tensor] = {}
         self._real: Dict[Tuple[str, torch.dtype], torch.Tensor] = {}
@@ -191,11 +206,12 @@ class HybridNetTopology:
                 d["adj"].data_ptr(), d["own_slot"].data_ptr(), self.ML, self.veh_cap, self.NCAP, len(self.groups), len(grp_lane),
                 len(self.routes), ROUTE_LEN, self.MAXT, d["kind"].data_ptr(), d["mic_of"].data_ptr(), d["mic_lane"].data_ptr(),
                 d["cap_off"].data_ptr(), d["cap_lane"].data_ptr(), d["grp_off"].data_ptr(), d["grp_lane"].data_ptr(),
-                d["routes"].data_ptr())
+                d["routes"].data_ptr(), d["src"].data_ptr() if self.sources else None)
         s = self.ML * self.veh_cap
-        self.A_P, self.A_V, self.A_A, self.A_RID, self.A_CUR = 0, s, 2 * s, 3 * s, 4 * s
-        self.A_FRONT = 5 * s; self.A_CNT = self.A_FRONT + self.ML; self.A_NSP = self.A_CNT + self.ML
-        self.A_CAP = self.A_NSP + self.ML; self.A_RMS = self.A_CAP + self.NCAP; self.AUX = self.A_RMS + 2
+        self.A_P, self.A_V, self.A_A, self.A_RID, self.A_CUR, self.A_PID = 0, s, 2 * s, 3 * s, 4 * s, 5 * s
+        self.A_FRONT = 6 * s; self.A_CNT = self.A_FRONT + self.ML; self.A_NSP = self.A_CNT + self.ML
+        self.A_CAP = self.A_NSP + self.ML; self.A_RMS = self.A_CAP + self.NCAP; self.A_DRAW = self.A_RMS + 2
+        self.AUX = self.A_DRAW + 1
 
     # ------------------------------------------------------------------ builders
     @classmethod
@@ -214,6 +230,7 @@ class HybridNetTopology:
     def struct_ptr(self):
         if self.device.type != "cuda":
             raise RuntimeError("the network rollout runs on CUDA only (no CPU fallback)")
+        self._sync_routes()
         return ctypes.byref(self._struct)
 
     def real(self, name: str, dtype) -> torch.Tensor:
@@ -232,7 +249,8 @@ class HybridNetTopology:
         return torch.tensor(rows, dtype=torch.int32, device=self.device)
 
     def route_id(self, path: Sequence[int]) -> int:
-        """Id of a vehicle route given as the reference's lane list: cut after the first macro lane."""
+        """Id of a vehicle route given as the reference's lane list: cut after the first macro lane.  With
+        ``enumerate_routes=False`` an unknown route is registered (the device table is re-uploaded before the next launch)."""
         cut = []
         for l in path:
             if l < 0:
@@ -240,7 +258,22 @@ class HybridNetTopology:
             cut.append(int(l))
             if not self.kind[l]:
                 break
-        return self.route_index[tuple(cut)]
+        key = tuple(cut)
+        if key not in self.route_index:
+            if self.enumerate_routes:
+                raise KeyError(key)
+            assert 1 <= len(key) <= ROUTE_LEN and self.kind[key[0]] == 1
+            self.route_index[key] = len(self.routes); self.routes.append(key)
+            self._routes_dirty = True
+        return self.route_index[key]
+
+    def _sync_routes(self):
+        if getattr(self, "_routes_dirty", False) and self.device.type == "cuda":
+            rows = [x for r in self.routes for x in (list(r) + [-1] * (ROUTE_LEN - len(r)))]
+            self._dev["routes"] = torch.tensor(rows, dtype=torch.int32, device=self.device)
+            self._struct.routes = self._dev["routes"].data_ptr()
+            self._struct.NR = len(self.routes)
+            self._routes_dirty = False
 
     def random_spawn_routes(self, R: int, max_spawn: int, generator: Optional[torch.Generator] = None) -> torch.Tensor:
         """[R][ML][max_spawn] int32: for every future spawn a random walk as create_random_route draws it (uniform next lane
@@ -269,22 +302,24 @@ class HybridNetTopology:
         o[..., 1] = umax                      # ARZ.FullQ(u_max), model/macro/_arz.py:59-63
         return o
 
-    def make_aux0(self, R: int, dtype, p0=None, v0=None, a0=None, route0=None, count0=None, capacitor0=None) -> torch.Tensor:
+    def make_aux0(self, R: int, dtype, p0=None, v0=None, a0=None, route0=None, count0=None, capacitor0=None,
+                  pid0=None) -> torch.Tensor:
         """Initial ``aux`` rows.  p0, v0, a0 [R][ML][cap]: initial vehicles of every micro lane, HEAD FIRST (the reverse of
-        ``lane.curr_vehicle``); route0 [ML][cap] route ids (``route_id``); count0 [ML]; capacitor0 [R][NCAP].  Differentiable
-        wrt p0, v0, a0, capacitor0."""
+        ``lane.curr_vehicle``); route0 [ML][cap] route ids (``route_id``); pid0 [ML][cap] parameter-set ids (rows of
+        ``veh_params``; default 0); count0 [ML]; capacitor0 [R][NCAP].  Differentiable wrt p0, v0, a0, capacitor0."""
         dev, ML, cap = self.device, self.ML, self.veh_cap
         z = lambda *s: torch.zeros(s, dtype=dtype, device=dev)
         p0 = z(R, ML, cap) if p0 is None else p0.to(dtype)
         v0 = z(R, ML, cap) if v0 is None else v0.to(dtype)
         a0 = z(R, ML, cap) if a0 is None else a0.to(dtype)
         rid = z(ML, cap) if route0 is None else torch.as_tensor(route0, device=dev).to(dtype)
+        pid = z(ML, cap) if pid0 is None else torch.as_tensor(pid0, device=dev).to(dtype)
         cnt = z(ML) if count0 is None else torch.as_tensor(count0, device=dev).to(dtype)
         assert float(cnt.max()) <= cap if ML else True
         capac = z(R, self.NCAP) if capacitor0 is None else capacitor0.to(dtype)
         ex = lambda t: t.reshape(1, -1).expand(R, -1)
-        return torch.cat([p0.reshape(R, -1), v0.reshape(R, -1), a0.reshape(R, -1), ex(rid), z(R, ML * cap), z(R, ML), ex(cnt),
-                          z(R, ML), capac, z(R, 2)], dim=1).contiguous()
+        return torch.cat([p0.reshape(R, -1), v0.reshape(R, -1), a0.reshape(R, -1), ex(rid), z(R, ML * cap), ex(pid), z(R, ML), ex(cnt),
+                          z(R, ML), capac, z(R, 3)], dim=1).contiguous()
 
 
 class HybRolloutFn(torch.autograd.Function):
@@ -292,8 +327,8 @@ class HybRolloutFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, r0, y0, u0, own0, sig, incoming, aux0, topo: HybridNetTopology, route, spawn_route, veh_par, umax, dt,
-                steps, soft, flags, ueq0=None):
-        dev = _lib.require_cuda(r0, y0, u0, own0, sig, incoming, aux0, route, spawn_route, flags)
+                steps, soft, flags, ueq0=None, src_rand=None):
+        dev = _lib.require_cuda(r0, y0, u0, own0, sig, incoming, aux0, route, spawn_route, flags, src_rand)
         ctx.set_materialize_grads(False)      # an output nobody differentiates stays None in backward (no zero-filled history)
         c = lambda t: None if t is None else t.contiguous()
         r0, y0, u0, own0, sig, incoming, aux0, route, spawn_route = map(c, (r0, y0, u0, own0, sig, incoming, aux0, route, spawn_route))
@@ -313,33 +348,40 @@ class HybRolloutFn(torch.autograd.Function):
             assert spawn_route.dtype == torch.int32 and spawn_route.shape[-2] == topo.ML
             KS = int(spawn_route.shape[-1])
             sp_rep = int(spawn_route.dim() == 3 and spawn_route.shape[0] == R and R > 1)
-        assert spawn_route is not None or topo.NCAP == 0
+        assert spawn_route is not None or (topo.NCAP == 0 and not topo.sources)
+        par = torch.as_tensor(veh_par, dtype=dtype, device=dev).reshape(-1, 6).contiguous()      # [NP, 6] parameter sets
+        n_rand, rand_rep = 0, 0
+        if topo.sources:
+            assert src_rand is not None and src_rand.dtype == dtype, "waiting-list sources consume uniform draws (src_rand)"
+            src_rand = src_rand.contiguous()
+            n_rand = int(src_rand.shape[-1])
+            rand_rep = int(src_rand.dim() == 2 and src_rand.shape[0] == R and R > 1)
         if own0 is None:
             own0 = topo.default_own(R, dtype, umax)
         hist = torch.empty((steps + 1, R, 4, NC), dtype=dtype, device=dev)
         ownh = torch.empty((steps + 1, R, max(topo.n_own, 1), 2), dtype=dtype, device=dev)
         auxh = torch.empty((steps + 1, R, topo.AUX), dtype=dtype, device=dev)
         headh = torch.empty((steps, R, max(topo.ML, 1), 2), dtype=dtype, device=dev)
-        par = (ctypes.c_double * 6)(*veh_par) if dtype == torch.float64 else (ctypes.c_float * 6)(*veh_par)
         lib = _lib.load()
         assert lib.dhts_hyb_aux_size(topo.struct_ptr()) == topo.AUX
         fn = getattr(lib, "dhts_hyb_rollout_fwd_" + suffix(dtype))
         with torch.cuda.device(dev):
             check(fn(topo.struct_ptr(), ptr(topo.real("dx", dtype)), ptr(topo.real("lane_len", dtype)), ptr(route), per_rep,
-                     ptr(spawn_route), sp_rep, KS, ptr(sig), ptr(incoming), par, creal(dtype, umax), creal(dtype, dt), steps, R,
+                     ptr(spawn_route), sp_rep, KS, ptr(sig), ptr(incoming), ptr(par), int(par.shape[0]), creal(dtype, topo.veh_len),
+                     ptr(src_rand if topo.sources else None), n_rand, rand_rep, creal(dtype, umax), creal(dtype, dt), steps, R,
                      topo.mode, int(bool(soft)), ptr(r0), ptr(y0), ptr(u0), ptr(c(ueq0)), ptr(own0 if topo.n_own else None), ptr(aux0),
                      ptr(hist), ptr(ownh if topo.n_own else None), ptr(auxh), ptr(headh if topo.ML else None), ptr(flags),
                      stream_ptr(dev)), "dhts_hyb_rollout_fwd")
-        ctx.save_for_backward(hist, ownh, auxh, sig, incoming, route, spawn_route)
-        ctx.cfg = (topo, per_rep, sp_rep, KS, list(veh_par), float(umax), float(dt), steps, int(bool(soft)), R)
+        ctx.save_for_backward(hist, ownh, auxh, sig, incoming, route, spawn_route, par, src_rand if topo.sources else None)
+        ctx.cfg = (topo, per_rep, sp_rep, KS, n_rand, rand_rep, float(umax), float(dt), steps, int(bool(soft)), R)
         ctx.flags = flags
         ctx.mark_non_differentiable(headh)
         return hist, auxh, headh
 
     @staticmethod
     def backward(ctx, g_hist, g_auxh, _g_head):
-        hist, ownh, auxh, sig, incoming, route, spawn_route = ctx.saved_tensors
-        topo, per_rep, sp_rep, KS, veh_par, umax, dt, steps, soft, R = ctx.cfg
+        hist, ownh, auxh, sig, incoming, route, spawn_route, par, src_rand = ctx.saved_tensors
+        topo, per_rep, sp_rep, KS, n_rand, rand_rep, umax, dt, steps, soft, R = ctx.cfg
         dev, dtype = hist.device, hist.dtype
         NC, L = topo.NC, topo.L
         g_states = g_hist[1:].contiguous() if (g_hist is not None and steps > 0) else None
@@ -350,11 +392,11 @@ class HybRolloutFn(torch.autograd.Function):
         g_sig = torch.zeros((R, steps, L), dtype=dtype, device=dev) if itscp else None
         g_inc = torch.zeros((R, steps, L), dtype=dtype, device=dev) if itscp else None
         g_aux0 = torch.zeros((R, topo.AUX), dtype=dtype, device=dev)
-        par = (ctypes.c_double * 6)(*veh_par) if dtype == torch.float64 else (ctypes.c_float * 6)(*veh_par)
         fn = getattr(_lib.load(), "dhts_hyb_rollout_bwd_" + suffix(dtype))
         with torch.cuda.device(dev):
             check(fn(topo.struct_ptr(), ptr(topo.real("dx", dtype)), ptr(topo.real("lane_len", dtype)), ptr(route), per_rep,
-                     ptr(spawn_route), sp_rep, KS, ptr(sig), ptr(incoming), par, creal(dtype, umax), creal(dtype, dt), steps, R,
+                     ptr(spawn_route), sp_rep, KS, ptr(sig), ptr(incoming), ptr(par), int(par.shape[0]), creal(dtype, topo.veh_len),
+                     ptr(src_rand), n_rand, rand_rep, creal(dtype, umax), creal(dtype, dt), steps, R,
                      topo.mode, soft, ptr(hist), ptr(ownh if topo.n_own else None), ptr(auxh), ptr(g_states), ptr(g_aux),
                      ptr(g_r0), ptr(g_y0), ptr(g_u0), ptr(g_own0 if topo.n_own else None), ptr(g_sig), ptr(g_inc), ptr(g_aux0),
                      ptr(ctx.flags), stream_ptr(dev)), "dhts_hyb_rollout_bwd")
@@ -365,7 +407,7 @@ class HybRolloutFn(torch.autograd.Function):
             g_aux0 = g_aux0 + g_auxh[0] * m
         need = ctx.needs_input_grad
         out = (g_r0, g_y0, g_u0, g_own0[:, :topo.n_own] if topo.n_own else None, g_sig, g_inc, g_aux0)
-        return tuple(g if need[i] else None for i, g in enumerate(out)) + (None,) * 10
+        return tuple(g if need[i] else None for i, g in enumerate(out)) + (None,) * 11
 
 
 class HybridStates:
@@ -430,23 +472,25 @@ class HybridStates:
 
 
 def hybrid_rollout(topo: HybridNetTopology, r0, u0, umax: float, dt: float, steps: int, *, sig=None, incoming=None, route=None,
-                   spawn_route=None, own0=None, aux0=None, soft: bool = True, veh_params: Optional[Sequence[float]] = None,
-                   flags: Optional[_lib.Flags] = None) -> HybridStates:
+                   spawn_route=None, own0=None, aux0=None, soft: bool = True, veh_params=None,
+                   flags: Optional[_lib.Flags] = None, src_rand=None) -> HybridStates:
     """`steps` x RoadNetwork.forward over R replicas of a connected hybrid network.
 
     r0, u0 [R, NC] density / speed of the macro cells, lane by lane; sig, incoming [R, steps, L] (ITSCP mode);
     route [steps, 2, L] or [R, steps, 2, L] int32 MacroRoute per step (``topo.route_table``); spawn_route [ML, KS] or
     [R, ML, KS] int32 (``topo.random_spawn_routes`` / ``topo.route_id``); aux0 from ``topo.make_aux0`` (default: no
-    vehicles, empty capacitors); veh_params (a_max, a_pref, v_target, s0, T, length), default
-    ``default_micro_vehicle(umax)``."""
+    vehicles, empty capacitors); veh_params [6] or [NP, 6] parameter sets (a_max, a_pref, v_target, s0, T, length), default
+    ``default_micro_vehicle(umax)`` -- set 0 is what spawned vehicles get, ``make_aux0(pid0=...)`` names the sets of the
+    initial vehicles; src_rand [n] or [R, n]: the uniform draws of the waiting-list sources (``sources=True`` topologies)."""
     flags = flags or _lib.Flags(r0.device)
     R = r0.shape[0]
     if aux0 is None:
         aux0 = topo.make_aux0(R, r0.dtype)
-    par = list(veh_params) if veh_params is not None else default_vehicle_params(umax, topo.veh_len)
-    assert abs(par[5] - topo.veh_len) < 1e-12, "vehicle length is part of the topology (deposit footprint)"
+    par = torch.as_tensor(veh_params if veh_params is not None else default_vehicle_params(umax, topo.veh_len),
+                          dtype=torch.float64).reshape(-1, 6)
+    assert float((par[:, 5] - topo.veh_len).abs().max()) < 1e-12, "one vehicle length per network (road_network.py:60); it is part of the topology"
     ueq = umax * (1.0 - torch.sqrt(torch.clamp(r0, min=0.0) + EPSILON))
     y0 = r0 * (u0 - ueq)                           # set_r_u, _arz.py:82-86 (autograd: true derivative)
     hist, auxh, headh = HybRolloutFn.apply(r0, y0, u0, own0, sig, incoming, aux0, topo, route, spawn_route, par, float(umax),
-                                           float(dt), int(steps), bool(soft), flags.t)
+                                           float(dt), int(steps), bool(soft), flags.t, None, src_rand)
     return HybridStates(topo, hist, auxh, headh)

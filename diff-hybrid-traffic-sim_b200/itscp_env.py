@@ -12,11 +12,14 @@ returns the queue-length reward (_env.py:618-648,770-797) as a 0-dim tensor whos
 through the adjoint kernels.  ``rollout`` is the batched form: R candidate actions / inflow schedules / spawn-route
 draws at once (episodes of an epoch, scenario replicas of a multi-GPU run).
 
-Modes: ``macro`` (every lane a dMacroLane -> ``network.net_rollout``) and ``hybrid`` (lanes of interior
-intersections are dMicroLanes, _env.py:490-500 -> ``hybrid_network.hybrid_rollout``).  ``micro`` mode (plain
-MicroLanes fed from a stochastic host-side waiting list, _simulator.py:153-174) is not on the differentiable path
-and is rejected.  Rendering does not exist: ``info['img']`` is a list of ``None`` (what the reference returns when
-``render_eval`` is off, _env.py:728-742).
+Modes: ``macro`` (every lane a dMacroLane -> ``network.net_rollout``), ``hybrid`` (lanes of interior
+intersections are dMicroLanes, _env.py:490-500 -> ``hybrid_network.hybrid_rollout``) and ``micro`` (every lane a
+MicroLane, _env.py:484-488; ``run_itscp_micro.sh``): the same hybrid rollout over an all-micro network whose boundary
+lanes are fed from the waiting lists ``_make_micro_route`` fills (_env.py:202-219) by the stochastic rule of
+``ItscpRoadNetwork.setup_micro_boundary`` (_simulator.py:153-174).  The uniform draws of that rule are taken from
+``np.random`` in the reference's order and count, so a seeded episode -- and the ``np.random`` state it leaves
+behind -- match the reference's.  Rendering does not exist: ``info['img']`` is a list of ``None`` (what the
+reference returns when ``render_eval`` is off, _env.py:728-742).
 """
 from __future__ import annotations
 
@@ -174,9 +177,8 @@ class ItscpEnv:
         cfg = self.config
         if cfg["random_seed"] > 0:
             np.random.seed(cfg["random_seed"])
-        if cfg["mode"] not in ("macro", "hybrid"):
-            raise ValueError("headless ItscpEnv steps the differentiable modes 'macro' and 'hybrid' (mode 'micro' feeds plain "
-                             "MicroLanes from a stochastic waiting list and has no gradient path, _env.py:484-488)")
+        if cfg["mode"] not in ("macro", "micro", "hybrid"):
+            raise ValueError("mode must be 'macro', 'micro' or 'hybrid' (_env.py:480-500)")
         if self.device is None:
             if not torch.cuda.is_available():
                 raise RuntimeError("ItscpEnv steps CUDA kernels only (no CPU fallback)")
@@ -205,12 +207,19 @@ class ItscpEnv:
         n = self.num_intersection
         if cfg["mode"] == "hybrid":      # _env.py:490-500
             self.kind = [0 if (i.row == 0 or i.row == n - 1 or i.col == 0 or i.col == n - 1) else 1 for i in g.lanes]
+        elif cfg["mode"] == "micro":     # _env.py:484-488
+            self.kind = [1] * g.L
         else:
             self.kind = [0] * g.L
         self.hybrid = any(self.kind)
+        self.micro_mode = cfg["mode"] == "micro"
+        self.veh_cap = int(cfg["veh_cap"])
+        if self.micro_mode:              # a lane of length len holds at most len / vehicle_length + 1 vehicles bumper to bumper
+            self.veh_cap = max(self.veh_cap, int(max(l.length for l in g.lanes) / float(cfg["vehicle_length"])) + 3)
         if self.hybrid:
             self.topo = HybridNetTopology(self.kind, g.num_cell, g.dx, [l.length for l in g.lanes], g.links, self.device,
-                                          MODE_ITSCP, veh_cap=int(cfg["veh_cap"]), veh_len=float(cfg["vehicle_length"]))
+                                          MODE_ITSCP, veh_cap=self.veh_cap, veh_len=float(cfg["vehicle_length"]),
+                                          sources=self.micro_mode, enumerate_routes=not self.micro_mode)
         else:
             self.topo = g.topology(self.device)
         self.boundary = g.boundary_lanes()
@@ -218,7 +227,7 @@ class ItscpEnv:
         # (tail first, _env.py:676-716)
         t = self.topo
         order, is_cell = [], []
-        cap = int(cfg["veh_cap"]) if self.hybrid else 0
+        cap = self.veh_cap if self.hybrid else 0
         cell_off = t.cell_off
         mic = 0
         for l in range(g.L):
@@ -248,10 +257,36 @@ class ItscpEnv:
         self.macro_route_schedule = torch.tensor(tab, dtype=torch.int32, device=self.device)
 
     def _make_micro_route(self):
-        """Vehicles enter micro lanes only through macro->micro spawning in hybrid mode (every micro lane has a predecessor,
-        SURVEY section 8 C4); each spawn draws a random route (conversion.py:53-57).  The draws are made up front: R sets of
-        ``max_spawn`` routes per micro lane, re-drawn by ``resample_spawn_routes``."""
+        """_env.py:202-219: ``max_num_micro_vehicle_per_lane`` waiting vehicles with random routes for EVERY lane, in every
+        mode (same ``np.random.randint`` draws as ``create_random_route``, road_network.py:604-646).  Only micro mode reads
+        them (boundary lanes, _simulator.py:153-174: popped from the END of the list).  In hybrid mode vehicles enter micro
+        lanes through macro->micro spawning instead (every micro lane has a predecessor); each spawn
+        draws a random route (conversion.py:53-57): R sets of ``max_spawn`` routes per micro lane, re-drawn by
+        ``resample_spawn_routes``."""
         self._spawn_routes = None
+        K = int(self.config["max_num_micro_vehicle_per_lane"])
+        nxt = self.topo.next
+        self.waiting_route: List[List[List[int]]] = []
+        for lane_id in range(self.grid.L):
+            rows = []
+            for _ in range(K):
+                route, cur = [], lane_id
+                for _ in range(32):                              # MAX_ROUTE_LENGTH, road_network.py:15
+                    route.append(cur)
+                    cand = nxt[cur]
+                    if not cand:
+                        break
+                    i = i0 = int(np.random.randint(0, len(cand)))
+                    while cand[i] in route:
+                        i = (i + 1) % len(cand)
+                        if i == i0:
+                            break
+                    cur = cand[i]
+                rows.append(route)
+            self.waiting_route.append(rows)
+        if self.micro_mode:       # pop order: the k-th vehicle that enters lane l rides waiting_route[l][K - 1 - k]
+            ids = [[self.topo.route_id(r) for r in reversed(rows)] for rows in self.waiting_route]
+            self._wait_ids = torch.tensor(ids, dtype=torch.int32, device=self.device).reshape(self.grid.L, K)
 
     def resample_spawn_routes(self, R: int, generator: Optional[torch.Generator] = None):
         if self.hybrid:
@@ -303,9 +338,12 @@ class ItscpEnv:
 
     # ------------------------------------------------------------------ simulation + reward
     def rollout(self, action: torch.Tensor, differentiable: bool, incoming: Optional[torch.Tensor] = None,
-                spawn_routes: Optional[torch.Tensor] = None, keep_states: bool = False) -> torch.Tensor:
+                spawn_routes: Optional[torch.Tensor] = None, keep_states: bool = False,
+                src_rand: Optional[torch.Tensor] = None) -> torch.Tensor:
         """R episodes at once.  action [R, A] (any device / float dtype; gradients flow back to it); incoming [R, T, L]
-        (default: this env's schedule for every replica); spawn_routes [R, ML, KS] or [ML, KS].  Returns reward [R]."""
+        (default: this env's schedule for every replica); spawn_routes [R, ML, KS] or [ML, KS]; src_rand [n] or [R, n]
+        (micro mode): the uniform draws of the waiting-list sources -- default: taken from ``np.random`` exactly as the
+        reference's episode would (replica after replica).  Returns reward [R]."""
         cfg = self.config
         dev, dtype, T = self.device, self.dtype, self.num_timestep
         act = action.to(device=dev, dtype=dtype)
@@ -322,16 +360,31 @@ class ItscpEnv:
         veh_len = float(cfg["vehicle_length"])
         w = (topo.real("dx", dtype) if self.hybrid else topo.dx(dtype))[topo.lane_of_cell()] / veh_len
         if self.hybrid:
-            if spawn_routes is None:
+            rng_state = None
+            if self.micro_mode:
+                spawn_routes = self._wait_ids if spawn_routes is None else spawn_routes
+                if src_rand is None:      # one draw per boundary lane and frame at most; the unused tail is handed back below
+                    n_max = T * sum(topo.src)
+                    rng_state = np.random.get_state() if R == 1 else None
+                    src_rand = torch.tensor(np.random.random((R, n_max)), dtype=dtype, device=dev)
+            elif spawn_routes is None:
                 if self._spawn_routes is None or self._spawn_routes.shape[0] != R:
                     self.resample_spawn_routes(R)
                 spawn_routes = self._spawn_routes
             st = hybrid_rollout(topo, r0, u0, umax, dt, T, sig=sig, incoming=inc.contiguous(), route=self.macro_route_schedule,
-                                spawn_route=spawn_routes, soft=differentiable, flags=self.flags)
+                                spawn_route=spawn_routes, soft=differentiable, flags=self.flags,
+                                src_rand=src_rand.to(device=dev, dtype=dtype) if self.micro_mode else None)
+            if rng_state is not None:     # leave np.random where the reference's episode would have left it
+                used = int(st.aux[-1, 0, topo.A_DRAW].detach().round().item())
+                np.random.set_state(rng_state)
+                if used:
+                    np.random.random((used,))
+                self.last_draws = used
             cells = st.cells
             r = cells[1:, :, 0].transpose(0, 1); u = cells[1:, :, 2].transpose(0, 1)          # [R, T, NC]
             _, v, _, valid = st.by_rank()
             cap = topo.veh_cap
+            assert cap == self.veh_cap
             v = v[1:].transpose(0, 1); valid = valid[1:].transpose(0, 1)                      # [R, T, ML, cap] head first
             cnt = st.count[1:].transpose(0, 1).unsqueeze(-1)                                  # [R, T, ML, 1]
             slot = torch.arange(cap, device=dev)

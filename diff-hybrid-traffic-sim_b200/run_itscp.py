@@ -21,7 +21,7 @@ from .itscp_env import ItscpEnv, problem_1, problem_2, problem_3
 
 def main(argv=None):
     parser = argparse.ArgumentParser("Script to solve intersection signal control problem")
-    parser.add_argument("--mode", type=str, choices=["macro", "hybrid"], default="macro")
+    parser.add_argument("--mode", type=str, choices=["macro", "micro", "hybrid"], default="macro")
     parser.add_argument("--problem", type=int, choices=[1, 2, 3], default=1)
     parser.add_argument("--n_trial", type=int, default=5)
     parser.add_argument("--n_intersection", type=int, default=1)

@@ -334,12 +334,22 @@ int dhts_net_rollout_bwd_f32(const dhts_net_topology* topo, const float* dx, con
  *                    components of "may touch the same lane", ascending lane id inside a group
  *   routes [NR][RLEN] lane ids along a vehicle route (MicroRoute.route), -1 terminated
  *   cap   vehicle slots per micro lane;  MAXT  max cells one absorbed vehicle can overlap (ceil(len / min dx) + 1)
+ *   src [ML] or NULL (mode 1 only): 1 = micro lane without predecessor that is fed from a WAITING LIST, the stochastic
+ *                    source of ITSCP micro mode (ItscpRoadNetwork.setup_micro_boundary, _simulator.py:153-174): while
+ *                    the lane has room for a vehicle it consumes one uniform draw per step (lanes in id order) and a
+ *                    default vehicle enters at position 0 when the draw is below incoming[.][t][lane] and the lane's
+ *                    list (spawn_route row, KS entries, in pop order) is not exhausted
  * Per call (beyond dhts_net_rollout_*):
- *   lane_len [L];  veh_par [6] HOST array (a_max, a_pref, v_target, s0, T, length) of every vehicle
+ *   lane_len [L];  veh_len: the network's vehicle length (RoadNetwork.add_vehicle asserts one length, road_network.py:60)
+ *   veh_par [n_par][6] DEVICE array of IDM parameter sets (a_max, a_pref, v_target, s0, T, unused): every vehicle names
+ *                    its set (MicroVehicle's own attributes, road/vehicle/micro_vehicle.py:74-122); set 0 is what
+ *                    spawned / waiting-list vehicles get (default_micro_vehicle, :30-72)
  *   spawn_route [Rs][ML][KS] int32: route id of the k-th vehicle spawned into a micro lane (Rs = R or 1)
- *   aux0 [R][AUX] (AUX = dhts_hyb_aux_size): vehicles p, v, a, route id, route cursor, each [ML][cap] by ring slot;
- *                    ring front, count, spawn counter [ML]; capacitors [NCAP]; running-mean (sum, count) of the micro
- *                    signal (_simulator.py:255-262); integers stored as reals
+ *   src_rand [Rr][n_rand] (Rr = R or 1) or NULL: the uniform draws of the waiting-list sources in consumption order
+ *                    (np.random.random in the reference); DHTS_FLAG_VEH_OVERFLOW when a rollout needs more than n_rand
+ *   aux0 [R][AUX] (AUX = dhts_hyb_aux_size): vehicles p, v, a, route id, route cursor, parameter-set id, each [ML][cap]
+ *                    by ring slot; ring front, count, spawn counter [ML]; capacitors [NCAP]; running-mean (sum, count) of
+ *                    the micro signal (_simulator.py:255-262); number of source draws consumed; integers stored as reals
  *   hist [steps+1][R][4][NC] (r, y, u, stored u_eq);  own_hist;  aux_hist [steps+1][R][AUX];
  *   head_hist [steps][R][ML][2] or NULL: head deltas each micro lane used
  * Backward: g_states [steps][R][4][NC] or NULL;  g_aux [steps][R][AUX] or NULL (p, v, a entries of the vehicles that
@@ -365,30 +375,35 @@ typedef struct dhts_hyb_topology {
     const int* grp_off;
     const int* grp_lane;
     const int* routes;
+    const int* src;
 } dhts_hyb_topology;
 
 int dhts_hyb_aux_size(const dhts_hyb_topology* topo);
 int dhts_hyb_rollout_fwd_f64(const dhts_hyb_topology* topo, const double* dx, const double* lane_len, const int* route,
                              int route_per_replica, const int* spawn_route, int spawn_per_replica, int KS,
-                             const double* sig, const double* incoming, const double* veh_par, double umax, double dt, int steps,
+                             const double* sig, const double* incoming, const double* veh_par, int n_par, double veh_len,
+                             const double* src_rand, int n_rand, int rand_per_replica, double umax, double dt, int steps,
                              int R, int mode, int soft, const double* r0, const double* y0, const double* u0, const double* ueq0,
                              const double* own0, const double* aux0, double* hist, double* own_hist, double* aux_hist, double* head_hist, int* flags,
                              void* stream);
 int dhts_hyb_rollout_bwd_f64(const dhts_hyb_topology* topo, const double* dx, const double* lane_len, const int* route,
                              int route_per_replica, const int* spawn_route, int spawn_per_replica, int KS,
-                             const double* sig, const double* incoming, const double* veh_par, double umax, double dt, int steps,
+                             const double* sig, const double* incoming, const double* veh_par, int n_par, double veh_len,
+                             const double* src_rand, int n_rand, int rand_per_replica, double umax, double dt, int steps,
                              int R, int mode, int soft, const double* hist, const double* own_hist, const double* aux_hist,
                              const double* g_states, const double* g_aux, double* g_r0, double* g_y0, double* g_u0, double* g_own0,
                              double* g_sig, double* g_incoming, double* g_aux0, int* flags, void* stream);
 int dhts_hyb_rollout_fwd_f32(const dhts_hyb_topology* topo, const float* dx, const float* lane_len, const int* route,
                              int route_per_replica, const int* spawn_route, int spawn_per_replica, int KS,
-                             const float* sig, const float* incoming, const float* veh_par, float umax, float dt, int steps,
+                             const float* sig, const float* incoming, const float* veh_par, int n_par, float veh_len,
+                             const float* src_rand, int n_rand, int rand_per_replica, float umax, float dt, int steps,
                              int R, int mode, int soft, const float* r0, const float* y0, const float* u0, const float* ueq0,
                              const float* own0, const float* aux0, float* hist, float* own_hist, float* aux_hist, float* head_hist, int* flags,
                              void* stream);
 int dhts_hyb_rollout_bwd_f32(const dhts_hyb_topology* topo, const float* dx, const float* lane_len, const int* route,
                              int route_per_replica, const int* spawn_route, int spawn_per_replica, int KS,
-                             const float* sig, const float* incoming, const float* veh_par, float umax, float dt, int steps,
+                             const float* sig, const float* incoming, const float* veh_par, int n_par, float veh_len,
+                             const float* src_rand, int n_rand, int rand_per_replica, float umax, float dt, int steps,
                              int R, int mode, int soft, const float* hist, const float* own_hist, const float* aux_hist,
                              const float* g_states, const float* g_aux, float* g_r0, float* g_y0, float* g_u0, float* g_own0,
                              float* g_sig, float* g_incoming, float* g_aux0, int* flags, void* stream);

@@ -187,3 +187,68 @@ def test_f32_build_tracks_f64_on_a_short_horizon(dev):
     assert (a[1] == b[1]).all()
     assert np.abs(a[0] - b[0]).max() < 2e-4 * np.abs(a[0]).max()
     assert np.isfinite(b[2]).all() and relerr(b[2], a[2]) < 5e-2
+
+
+def test_per_vehicle_idm_parameters_match_live_reference(dev):
+    """Every vehicle with its OWN IDM parameter set (MicroVehicle.random_micro_vehicle, road/vehicle/micro_vehicle.py:74-122):
+    macro(10) -> micro -> micro -> macro(10) against tests/golden/hybrid_chain_pv_fp64.npz (live reference, 600 steps; five
+    heterogeneous initial vehicles that are handed from micro lane to micro lane and absorbed, nine default vehicles
+    spawned behind them).  Counts per step, final cells and vehicles, loss, gradients wrt lane 0 and wrt the initial
+    vehicle positions and speeds."""
+    from conftest import golden
+    from dhts_b200 import Flags
+    from dhts_b200.hybrid_network import HybridNetTopology, default_vehicle_params, hybrid_rollout
+    from dhts_b200.network import MODE_PLAIN
+    g = golden("hybrid_chain_pv_fp64")
+    N, dx, umax, dt, T = int(g["N"]), float(g["dx"]), float(g["umax"]), float(g["dt"]), int(g["T"])
+    cap = 12
+    topo = HybridNetTopology([0, 1, 1, 0], [N, 0, 0, N], [dx, 1.0, 1.0, dx], [N * dx] * 4, [(0, 1), (1, 2), (2, 3)], dev, MODE_PLAIN,
+                             veh_cap=cap)
+    assert topo.n_own == 4 and topo.NCAP == 1 and topo.ML == 2
+    gh = g["ghost_ru"]
+    own0 = t64(np.stack([gh[0], gh[2], gh[1], gh[3]])[None], dev)
+    r0 = t64(g["r0"].reshape(1, -1), dev, True); u0 = t64(g["u0"].reshape(1, -1), dev, True)
+    route = torch.tensor([[[-1, 0, -1, -1], [1, -1, -1, -1]]] * T, dtype=torch.int32, device=dev)
+    sp = torch.full((2, 32), topo.route_id([1, 2, 3]), dtype=torch.int32, device=dev)
+    n1, n2 = len(g["pos1"]), len(g["pos2"])
+    pad = lambda x: np.concatenate([x, np.zeros(cap - len(x))])
+    p0 = t64(np.stack([pad(g["pos1"]), pad(g["pos2"])])[None], dev, True)
+    v0 = t64(np.stack([pad(g["spd1"]), pad(g["spd2"])])[None], dev, True)
+    a0 = torch.full((1, 2, cap), 5.0, dtype=F64, device=dev)
+    route0 = np.zeros((2, cap)); route0[0, :] = topo.route_id([1, 2, 3]); route0[1, :] = topo.route_id([2, 3])
+    pid0 = np.zeros((2, cap)); pid0[0, :n1] = 1 + np.arange(n1); pid0[1, :n2] = 1 + n1 + np.arange(n2)
+    par = np.concatenate([[default_vehicle_params(umax)], g["par1"], g["par2"]])
+    aux0 = topo.make_aux0(1, F64, p0, v0, a0, route0, [n1, n2], pid0=pid0)
+    flags = Flags(dev)
+    st = hybrid_rollout(topo, r0, u0, umax, dt, T, route=route, spawn_route=sp, own0=own0, aux0=aux0, veh_params=par, flags=flags)
+    flags.check()
+    cnt = st.count[1:, 0].cpu().numpy()
+    assert (cnt == g["cnt_hist"]).all()
+    nsp = st.aux[1:, 0, topo.A_NSP].detach().round().long().cpu().numpy() + n1 + n2
+    assert (nsp == g["nspawn_hist"]).all() and nsp[-1] == 14
+    cells = st.cells[T, 0].detach().cpu().numpy()
+    assert np.abs(cells[:, :N] - g["lane0"]).max() < 1e-9 and np.abs(cells[:, N:] - g["lane3"]).max() < 1e-9
+    p, v, a, valid = st.by_rank()
+    w = g["w_veh"]
+    loss = (st.cells[T, 0, 0, N:] * t64(g["w_r"], dev)).sum() + (st.cells[T, 0, 2, N:] * t64(g["w_u"], dev)).sum()
+    for m, key in ((0, "veh1"), (1, "veh2")):
+        n = int(cnt[-1, m])
+        tail_first = lambda x: torch.flip(x[T, 0, m, :n], dims=[0])
+        veh = torch.stack([tail_first(p), tail_first(v), tail_first(a)], -1)
+        assert veh.shape[0] == g[key].shape[0] and np.abs(veh.detach().cpu().numpy() - g[key][:, :3]).max() < 1e-9
+        for i in range(n):
+            loss = loss + float(w[2 * i % 8]) * veh[i, 0] * 0.01 + float(w[(2 * i + 1) % 8]) * veh[i, 1] * 0.01
+    assert abs(float(loss) - float(g["loss"])) < 1e-9
+    loss.backward()
+    flags.check()
+    gr, gu = r0.grad[0].cpu().numpy(), u0.grad[0].cpu().numpy()
+    assert relerr(gr[:N], g["g_r0_lane0"]) < 1e-8 and relerr(gu[:N], g["g_u0_lane0"]) < 1e-8
+    assert relerr(gr[N:], g["g_r0_lane3"]) < 1e-8 and relerr(gu[N:], g["g_u0_lane3"]) < 1e-8
+    gp, gv = p0.grad[0].cpu().numpy(), v0.grad[0].cpu().numpy()
+    assert relerr(gp[0, :n1], g["g_pos1"]) < 1e-8 and relerr(gv[0, :n1], g["g_spd1"]) < 1e-8
+    assert relerr(gp[1, :n2], g["g_pos2"]) < 1e-8 and relerr(gv[1, :n2], g["g_spd2"]) < 1e-8
+    assert np.abs(g["g_pos1"]).max() > 0
+    # one parameter set for everybody is a different trajectory (the parameters matter)
+    st1 = hybrid_rollout(topo, r0.detach(), u0.detach(), umax, dt, T, route=route, spawn_route=sp, own0=own0,
+                         aux0=topo.make_aux0(1, F64, p0.detach(), v0.detach(), a0, route0, [n1, n2]), flags=Flags(dev))
+    assert not (st1.count[1:, 0].cpu().numpy() == g["cnt_hist"]).all()

@@ -38,7 +38,7 @@ def test_aux_layout_and_initial_rows():
     G = fixture_case("h")
     _, topo = build(G, "cpu", veh_cap=4)
     s = topo.ML * topo.veh_cap
-    assert topo.AUX == 5 * s + 3 * topo.ML + topo.NCAP + 2
+    assert topo.AUX == 6 * s + 3 * topo.ML + topo.NCAP + 3
     p0 = torch.arange(2 * s, dtype=torch.float64).reshape(2, topo.ML, topo.veh_cap)
     cnt = [1] * topo.ML
     aux = topo.make_aux0(2, torch.float64, p0=p0, count0=cnt)

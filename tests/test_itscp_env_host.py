@@ -36,8 +36,9 @@ def test_env_surface_matches_run_py_configuration():
     # every route of the fixture's spawned vehicles is known to the topology
     tab = c4_spawn_routes(G, env.topo)
     assert tab.max() < len(env.topo.routes)
-    with pytest.raises(ValueError):
-        e2 = c4_env(G, "cpu", mode="micro")
+    # micro mode (run_itscp_micro.sh) builds an all-micro network whose boundary lanes are waiting-list sources
+    e2 = c4_env(G, "cpu", mode="micro")
+    assert e2.micro_mode and e2.topo.NC == 0 and e2.topo.ML == 144 and sum(e2.topo.src) == 12
 
 
 def test_no_cpu_fallback():
