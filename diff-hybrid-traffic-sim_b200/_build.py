@@ -48,7 +48,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
             continue
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
         objs.append(obj)
-        cmd = [nvcc] + ccbin + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
+        extra = os.environ.get("DHTS_NVCC_EXTRA", "").split()      # diagnosis builds, e.g. -DDHTS_PHASE_TIMING (scripts/hyb_phases.py)
+        cmd = [nvcc] + ccbin + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)))
     for cmd, p in procs:
         out, _ = p.communicate()

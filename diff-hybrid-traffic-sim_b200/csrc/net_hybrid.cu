@@ -40,13 +40,30 @@
 // neighbours took from it (fixed order, no atomics).
 #include <cmath>
 #include <cuda_pipeline.h>
-#include "dhts_net.cuh"
+#include "dhts_net_if.cuh"
 #include "dhts_idm.cuh"
+
+// Diagnosis build (-DDHTS_PHASE_TIMING, scripts/hyb_phases.py): thread 0 of CTA 0 accumulates the cycles between the phase
+// boundaries of a step (barrier waits included, i.e. the wall time of each phase as the slowest thread sets it).
+#ifdef DHTS_PHASE_TIMING
+__device__ unsigned long long g_phase_cycles[32];
+#define DHTS_PT_DECL unsigned long long pt_last_ = clock64();
+#define DHTS_PT(i) if (threadIdx.x == 0 && blockIdx.x == 0) { const unsigned long long now_ = clock64(); atomicAdd(&g_phase_cycles[i], now_ - pt_last_); pt_last_ = now_; }
+extern "C" __attribute__((visibility("default"))) int dhts_debug_phase_cycles(unsigned long long* out32) {
+    cudaDeviceSynchronize();
+    unsigned long long z[32] = {0};
+    if (cudaMemcpyFromSymbol(out32, g_phase_cycles, sizeof(z)) != cudaSuccess) return 1;
+    return cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z)) != cudaSuccess;
+}
+#else
+#define DHTS_PT_DECL
+#define DHTS_PT(i)
+#endif
 
 namespace dhts {
 
 constexpr int FLAG_VEH_OVERFLOW = 16;
-constexpr int HYB_THREADS_MAX = 256;
+constexpr int HYB_THREADS_MAX = 512;
 
 struct AuxL { int P, V, A, RID, CUR, PID, FRONT, CNT, NSP, CAP, RMS, DRAW, AUX; };
 __host__ __device__ inline AuxL aux_layout(int ML, int cap, int NCAP) {
@@ -77,6 +94,7 @@ template <typename T> struct HybArgs {
     const T* rnd;             // [Rr][NRAND] the uniform draws of the waiting-list source, in consumption order
     long long rnd_stride;     // 0 when shared by all replicas
     int NRAND;
+    int prefetch;             // adjoint: stream the stored rows one step ahead (needs a second set of state buffers in shared memory)
     T head_dp0, head_dv0;     // DEFAULT_HEAD_POSITION_DELTA / DEFAULT_HEAD_SPEED_DELTA (_micro_lane.py:14-15)
     AuxL ax;
 };
@@ -188,42 +206,64 @@ template <typename T> struct HybSm {
     T* headd;     // [ML][2] head deltas the IDM step used
     T* mid;       // adjoint kernel: (r, y, u) x NC between update and conversions
     ConvLog<T> log;
-    int* order;   // [L] thread -> lane assignment: macro lanes by decreasing number of cells, then the micro lanes
+    NetTabs<T> tb;   // interface / cell -> lane tables of the macro lanes (dhts_net_if.cuh)
+    T* gh;        // [2][L][2] final ghost (r, u) of the macro lanes at the current step
+    T* flux;      // [NI][2] fluxes of the macro lanes' interfaces
+    T* ab;        // adjoint kernel: [NI][4] (A^T w, B^T w) per interface; lives in st[1] (dead once the replay is done) + a tail
+    SideTab<T> sd;   // adjoint kernel: side records of the current step
     int* walk;    // [NGL][6] lookups of the conversion walk of the current step (lane, kind, next / micro index, capacitor, ...)
     int* goff;    // [NG+1] group offsets (copy of grp_off)
     T* walkT;     // [NGL] length of the lane the walk asks about (macro: the micro successor; micro: the lane itself)
     IdmPar<T>* par;  // [NP] parameter sets with their derived constants
     int* srcf;    // [ML] waiting-list source: the lane had room at this step (one uniform draw consumed)
     int* srcs;    // [ML] waiting-list source: ring slot of the vehicle that entered at this step, -1 = none
+    HeadRec<T>* hrec;   // [ML] head-vehicle record of the current step (phase 0), read again by the IDM step and its adjoint
+    int* gflag;   // [NG] the group has a conversion candidate at this step (a pop or a spawn may happen): serial walk
+    int* gof;     // [NGL] group of a group lane
 };
 
-// Lanes sorted (stably) so that the threads of a warp do the same kind of work: macro lanes of equal length together,
-// micro lanes together.  Every thread calls it once per kernel; ends with a block barrier.
-template <typename T> __device__ __forceinline__ void hyb_lane_order(const HybArgs<T>& a, int* order, IdmPar<T>* par) {
-    const NetArgs<T>& n = a.n;
-    for (int i = threadIdx.x; i < a.NP; i += blockDim.x) {      // parameter sets with the constants of _idm.py:31-40
+// Parameter sets with their derived constants and the interface tables of the macro lanes.  Every thread calls it once
+// per kernel; ends with a block barrier.
+template <typename T> __device__ __forceinline__ void hyb_init(const HybArgs<T>& a, const HybSm<T>& s) {
+    for (int i = threadIdx.x; i < a.NP; i += blockDim.x) {      // the constants of _idm.py:31-40
         const T* q = a.par_tab + (size_t)i * 6;
         IdmPar<T> k;
         k.a_max = q[0]; k.v_t_inv = T(1) / q[2]; k.s0 = q[3]; k.tp = q[4]; k.len = a.vlen;
         k.sab2_inv = T(1) / (T(2) * t_sqrt(q[0] * q[1]));
-        par[i] = k;
+        s.par[i] = k;
     }
-    for (int l = threadIdx.x; l < n.L; l += blockDim.x) {
-        const int key = n.kind[l] ? -1 : n.cell_off[l + 1] - n.cell_off[l];
-        int rank = 0;
-        for (int j = 0; j < n.L; j++) {
-            const int kj = n.kind[j] ? -1 : n.cell_off[j + 1] - n.cell_off[j];
-            rank += (kj > key) || (kj == key && j < l);
-        }
-        order[rank] = l;
+    // the static part of the conversion walk's lookups (phase 2a fills in what depends on the step's MacroRoute)
+    const NetArgs<T>& n = a.n;
+    for (int gi = threadIdx.x; gi < a.NGL; gi += blockDim.x) {
+        const int l = a.grp_lane[gi];
+        int* w = s.walk + gi * 6;
+        w[0] = l; w[1] = n.kind[l]; w[2] = -1; w[3] = -1; w[4] = -1; w[5] = n.cell_off[l + 1] - 1;
+        s.walkT[gi] = T(0);
+        if (w[1] == 1) { w[2] = a.mic_of[l]; s.walkT[gi] = a.lane_len[l]; }
     }
-    __syncthreads();
+    for (int g = threadIdx.x; g <= a.NG; g += blockDim.x) {
+        s.goff[g] = a.grp_off[g];
+        if (g < a.NG) for (int gi = a.grp_off[g]; gi < a.grp_off[g + 1]; gi++) s.gof[gi] = g;
+    }
+    net_tabs_init(a.n, s.tb);
 }
 
+// The per-step input rows (MacroRoute, signals, inflow) of replica b at step t.  (Streaming them into shared memory one step
+// ahead was measured: no change of the step latency at one replica, 20 % slower at 256 replicas -- the extra cp.async and
+// barrier per step cost more than the L2 round trips they hide.)
+template <typename T> struct StepRows { const int* rt; const T* sig; const T* inc; };
+template <typename T> __device__ __forceinline__ StepRows<T> global_rows(const NetArgs<T>& n, int b, int t) {
+    StepRows<T> r;
+    r.rt = n.route ? n.route + (size_t)b * n.route_stride + (size_t)t * 2 * n.L : nullptr;
+    r.sig = n.sig ? n.sig + ((size_t)b * n.T_steps + t) * n.L : nullptr;
+    r.inc = n.incoming ? n.incoming + ((size_t)b * n.T_steps + t) * n.L : nullptr;
+    return r;
+}
 // One simulation step of replica b: state `p` -> state `p ^ 1` of the double buffers.  All threads of the CTA call it.
 // REC: keep the state between update and conversions (s.mid) and the conversion events (s.log).
 template <typename T, bool REC>
-__device__ __forceinline__ void hyb_step(const HybArgs<T>& a, const HybSm<T>& s, int b, int t, int p, unsigned& fl, int& ncol) {
+__device__ __forceinline__ void hyb_step(const HybArgs<T>& a, const HybSm<T>& s, int b, int t, int p, const StepRows<T>& rows,
+                                         unsigned& fl, int& ncol) {
     const NetArgs<T>& n = a.n;
     const AuxL& x = a.ax;
     const int NC = n.NC, L = n.L;
@@ -231,12 +271,11 @@ __device__ __forceinline__ void hyb_step(const HybArgs<T>& a, const HybSm<T>& s,
     T* nr = s.st[p ^ 1]; T* ny = nr + NC; T* nu = ny + NC; T* ne = nu + NC;
     const T* ownc = s.own[p]; T* ownn = s.own[p ^ 1];
     const T* auxc = s.aux[p]; T* auxn = s.aux[p ^ 1];
-    const int* rt = n.route ? n.route + (size_t)b * n.route_stride + (size_t)t * 2 * L : nullptr;
-    const T* sig_t = n.sig ? n.sig + ((size_t)b * n.T_steps + t) * L : nullptr;
-    const T* inc_t = n.incoming ? n.incoming + ((size_t)b * n.T_steps + t) * L : nullptr;
-    const T inv_umax = T(1) / n.umax, inv15 = T(1) / (T(1.5) * n.umax), inv_dt = T(1) / n.dt;
+    const int* rt = rows.rt; const T* sig_t = rows.sig; const T* inc_t = rows.inc;
+    const T inv_dt = T(1) / n.dt;
     const bool blend = n.mode == 1 && n.soft && a.ML > 0;
     const T vlen = a.vlen;
+    DHTS_PT_DECL
     // ---- phase S: waiting-list sources (ItscpRoadNetwork.setup_micro_boundary, _simulator.py:153-174).  A boundary micro
     // lane with room for a vehicle consumes ONE uniform draw -- lanes in id order within a step, so the draw a lane gets
     // depends on how many lanes before it had room -- and, if the draw is below the scheduled inflow and its waiting list
@@ -282,57 +321,35 @@ __device__ __forceinline__ void hyb_step(const HybArgs<T>& a, const HybSm<T>& s,
         }
         __syncthreads();
     }
-    // ---- phase 0: final_signal of every head vehicle (the running mean visits the micro lanes in id order)
-    if (blend) {
-        for (int m = threadIdx.x; m < a.ML; m += blockDim.x) {
-            const bool has = auxc[x.CNT + m] > T(0);
-            T fin = T(0);
-            if (has) fin = head_rec(a, a.mic_lane[m], m, auxc, sig_t).fin;
-            s.fsig[2 * m] = fin; s.fsig[2 * m + 1] = has ? T(1) : T(0);
-        }
-        __syncthreads();
+    // ---- phase 0: the head vehicle's record of every micro lane, once per step (final_signal enters the running mean,
+    // which visits the micro lanes in id order); the aux row is carried over wholesale, phase 1 writes what changes
+    for (int m = (int)blockDim.x - 1 - (int)threadIdx.x; m < a.ML; m += blockDim.x) {
+        const bool has = auxc[x.CNT + m] > T(0);
+        T fin = T(0);
+        if (has) { s.hrec[m] = head_rec(a, a.mic_lane[m], m, auxc, sig_t); fin = s.hrec[m].fin; }
+        s.fsig[2 * m] = fin; s.fsig[2 * m + 1] = has ? T(1) : T(0);
     }
-    // ---- phase 1: every lane takes its step from the state before the step (Jacobi)
+    for (int c = threadIdx.x; c < x.AUX; c += blockDim.x) auxn[c] = auxc[c];
+    __syncthreads();
+    DHTS_PT(0)      // phase S + 0
+    // ---- phase 1: every lane takes its step from the state before the step (Jacobi).  Macro lanes in three sub-phases
+    // (dhts_net_if.cuh): ghosts per (side, lane), fluxes per interface, update per cell.  The micro lanes -- one thread each,
+    // taken from the far end of the CTA so that they do not queue behind the ghost threads -- run beside the ghosts.
     bool bad = false, bad_route = false;
-    for (int li = threadIdx.x; li < L; li += blockDim.x) {
-        const int l = s.order[li];
-        if (n.kind[l] == 0) {
-            const int c0 = n.cell_off[l], N = n.cell_off[l + 1] - c0;
-            const T dxl = n.dx[l], cc = n.dt / dxl;
-            const Side<T> sl = resolve_side(n, l, 0, rt, cr, cu, ownc, sig_t, inc_t, bad_route);
-            const Side<T> sr = resolve_side(n, l, 1, rt, cr, cu, ownc, sig_t, inc_t, bad_route);
-            const int osl = n.own_slot[l], osr = n.own_slot[L + l];
-            if (osl >= 0) { ownn[2 * osl] = sl.fr; ownn[2 * osl + 1] = sl.fu; }
-            if (osr >= 0) { ownn[2 * osr] = sr.fr; ownn[2 * osr + 1] = sr.fu; }
-            Cell<T> Lc = ghost_cell<T, false>(sl.fr, sl.fu, n.umax);
-            T fpr = T(0), fpy = T(0);
-            for (int i = 0; i <= N; i++) {
-                const Cell<T> Rc = (i < N) ? derive_cell_stored<T, false>(cr[c0 + i], cy[c0 + i], cu[c0 + i], ce[c0 + i], true, n.umax)
-                                           : ghost_cell<T, false>(sr.fr, sr.fu, n.umax);
-                const Riem<T> o = riemann(Lc, Rc, n.umax, inv_umax, inv15, n.dt, dxl);
-                bad |= o.cfl_bad;
-                const T fr = o.r0 * o.u0, fy = o.y0 * o.u0;
-                if (i > 0) {
-                    const T r = cr[c0 + i - 1] + (fpr - fr) * cc;
-                    const T y = cy[c0 + i - 1] + (fpy - fy) * cc;
-                    nr[c0 + i - 1] = r; ny[c0 + i - 1] = y; nu[c0 + i - 1] = compute_u(r, y, n.umax);
-                    ne[c0 + i - 1] = u_eq(r, n.umax);                        // set_r_y refreshes u and u_eq, _arz.py:88-92
-                }
-                fpr = fr; fpy = fy; Lc = Rc;
-            }
-            for (int k = a.cap_off[l]; k < a.cap_off[l + 1]; k++) auxn[x.CAP + k] = auxc[x.CAP + k];
-        } else {
-            const int m = a.mic_of[l];
+    for (int q = threadIdx.x; q < 2 * L; q += blockDim.x) {
+        const int side = q >= L, l = q - side * L;
+        if (n.kind[l]) continue;
+        const Side<T> sd = resolve_side(n, l, side, rt, cr, cu, ownc, sig_t, inc_t, bad_route);
+        s.gh[2 * q] = sd.fr; s.gh[2 * q + 1] = sd.fu;
+        const int os = n.own_slot[q];
+        if (os >= 0) { ownn[2 * os] = sd.fr; ownn[2 * os + 1] = sd.fu; }
+    }
+    for (int m = (int)blockDim.x - 1 - (int)threadIdx.x; m < a.ML; m += blockDim.x) {
+        {
             const int f = (int)auxc[x.FRONT + m], cnt = (int)auxc[x.CNT + m];
-            auxn[x.FRONT + m] = auxc[x.FRONT + m]; auxn[x.CNT + m] = auxc[x.CNT + m]; auxn[x.NSP + m] = auxc[x.NSP + m];
-            for (int q = 0; q < a.cap; q++) {
-                const int o = m * a.cap + q;
-                auxn[x.P + o] = auxc[x.P + o]; auxn[x.V + o] = auxc[x.V + o]; auxn[x.A + o] = auxc[x.A + o];
-                auxn[x.RID + o] = auxc[x.RID + o]; auxn[x.CUR + o] = auxc[x.CUR + o]; auxn[x.PID + o] = auxc[x.PID + o];
-            }
             T dp = a.head_dp0, dv = a.head_dv0, kc = T(0);
             if (cnt > 0) {
-                const HeadRec<T> h = head_rec(a, l, m, auxc, sig_t);
+                const HeadRec<T>& h = s.hrec[m];
                 dp = h.gdp; dv = h.gdv;
                 if (n.mode == 1) {
                     if (n.soft) {
@@ -369,39 +386,82 @@ __device__ __forceinline__ void hyb_step(const HybArgs<T>& a, const HybSm<T>& s,
             }
         }
     }
+    __syncthreads();
+    DHTS_PT(1)      // ghosts + micro lanes
+    bad |= net_fwd_flux<T>(n, s.tb, cr, cy, cu, ce, s.gh, s.flux);
+    __syncthreads();
+    DHTS_PT(2)      // fluxes
+    for (int c = threadIdx.x; c < NC; c += blockDim.x) {      // _macro_lane.py:83-114; set_r_y refreshes u and u_eq, _arz.py:88-92
+        const int l = s.tb.lane_of_cell[c];
+        const int it = s.tb.if_off[l] + (c - n.cell_off[l]);
+        const T cc = s.tb.cc[l];
+        const T r = fma(s.flux[2 * it] - s.flux[2 * it + 2], cc, cr[c]);
+        const T y = fma(s.flux[2 * it + 1] - s.flux[2 * it + 3], cc, cy[c]);
+        nr[c] = r; ny[c] = y; nu[c] = compute_u(r, y, n.umax); ne[c] = u_eq(r, n.umax);
+    }
     // ---- phase 2a: the table lookups of the conversion walk, one thread per group lane.  The walk itself is serial
     // (lanes of a group in id order, one thread per group); from global memory each of its links -- group -> lane ->
     // kind -> route -> capacitor -> micro index -- is an L2 round trip, which made it half of a step's latency
     for (int gi = threadIdx.x; gi < a.NGL; gi += blockDim.x) {
-        const int l = a.grp_lane[gi];
         int* w = s.walk + gi * 6;
-        w[0] = l; w[1] = n.kind[l]; w[2] = -1; w[3] = -1; w[4] = -1; w[5] = n.cell_off[l + 1] - 1;
-        if (w[1] == 0) {
+        if (w[1] == 0) {      // macro lane: the micro lane the step's MacroRoute connects it to, and the capacitor that feeds it
+            const int l = w[0];
             const int nx = rt ? rt[L + l] : -1;
+            int k = -1, m2 = -1, nxm = -1;
             if (nx >= 0 && n.kind[nx] == 1) {
-                int k = -1;
                 for (int q = a.cap_off[l]; q < a.cap_off[l + 1]; q++) if (a.cap_lane[q] == nx) k = q;
-                w[2] = nx; w[3] = k; w[4] = a.mic_of[nx];
+                nxm = nx; m2 = a.mic_of[nx];
             }
+            w[2] = nxm; w[3] = k; w[4] = m2;
             s.walkT[gi] = nx >= 0 ? a.lane_len[nx] : T(0);
-        } else {
-            w[2] = a.mic_of[l];
-            s.walkT[gi] = a.lane_len[l];
         }
     }
-    for (int g = threadIdx.x; g <= a.NG; g += blockDim.x) s.goff[g] = a.grp_off[g];
+    for (int g = threadIdx.x; g < a.NG; g += blockDim.x) s.gflag[g] = 0;
     if (bad) fl |= FLAG_CFL;
     if (bad_route) fl |= FLAG_ROUTE;
     __syncthreads();
-    if (REC) {
-        for (int c = threadIdx.x; c < 3 * NC; c += blockDim.x) s.mid[c] = nr[c];
-        __syncthreads();
+    DHTS_PT(3)      // update + walk lookups
+    if (REC) for (int c = threadIdx.x; c < 3 * NC; c += blockDim.x) s.mid[c] = nr[c];
+    // ---- phase 2b: does a group have a conversion CANDIDATE at this step -- a head vehicle at the end of its lane, a
+    // capacitor that has collected a vehicle?  Pops and spawns are rare (a few per lane and episode); without a candidate
+    // the serial walk of the group would only add the step's flux to every capacitor, which its lanes do in parallel below.
+    for (int gi = threadIdx.x; gi < a.NGL; gi += blockDim.x) {
+        const int* w = s.walk + gi * 6;
+        bool cand = false;
+        if (w[1] == 0) {
+            if (w[2] >= 0 && w[3] >= 0) {      // a spawn needs a collected vehicle AND room on the micro lane (exact unless a pop of this step
+                const int m2 = w[4];           // empties that lane -- which flags the group by itself)
+                const int n2 = (int)auxn[x.CNT + m2];
+                const T space = n2 > 0 ? auxn[x.P + m2 * a.cap + ((int)auxn[x.FRONT + m2] + n2 - 1) % a.cap] - vlen * T(0.5) : s.walkT[gi];
+                cand = (auxn[x.CAP + w[3]] + nr[w[5]] * nu[w[5]] * n.dt >= vlen) && (space >= vlen);
+            }
+        } else {
+            const int m = w[2];
+            if ((int)auxn[x.CNT + m] > 0) cand = auxn[x.P + m * a.cap + (int)auxn[x.FRONT + m]] >= s.walkT[gi];
+        }
+        if (cand) s.gflag[s.gof[gi]] = 1;
     }
-    // ---- phase 2: conversions, one thread per group, lanes in id order (road_network.py:113-173)
+    __syncthreads();
+    DHTS_PT(4)      // candidates (+ mid copy)
+    // ---- phase 2: conversions (road_network.py:113-173).  Groups without a candidate: one thread per group lane.
+    for (int gi = threadIdx.x; gi < a.NGL; gi += blockDim.x) {
+        if (s.gflag[s.gof[gi]]) continue;
+        const int* w = s.walk + gi * 6;
+        int ev = EV_NONE, e2 = 0;
+        if (w[1] == 0 && w[2] >= 0 && w[3] >= 0) {                               // macro_to_micro without a spawn, conversion.py:15-73
+            const int k = w[3], c = w[5];
+            const T rl = nr[c], ul = nu[c];
+            auxn[x.CAP + k] = auxn[x.CAP + k] + rl * ul * n.dt;
+            ev = EV_CAP; e2 = k;
+            if (REC) { s.log.et[gi * (3 + a.MAXT)] = rl; s.log.et[gi * (3 + a.MAXT) + 1] = ul; }
+        }
+        if (REC) { int* q = s.log.ei + gi * 4; q[0] = ev; q[1] = 0; q[2] = e2; q[3] = 0; }
+    }
+    // Groups with a candidate: one thread per group, lanes in id order.
     for (int g = threadIdx.x; g < a.NG; g += blockDim.x) {
+        if (!s.gflag[g]) continue;
         for (int gi = s.goff[g]; gi < s.goff[g + 1]; gi++) {
             const int* w = s.walk + gi * 6;
-            const int l = w[0];
             int ev = EV_NONE, e1 = 0, e2 = 0, e3 = 0;
             if (w[1] == 0) {                                                     // conversion_macro
                 const int nx = w[2];
@@ -489,6 +549,11 @@ __device__ __forceinline__ void hyb_step(const HybArgs<T>& a, const HybSm<T>& s,
         }
     }
     __syncthreads();
+    DHTS_PT(5)      // conversions
+    DHTS_PT(6)      // (nothing: the cost of a marker itself)
+#ifdef DHTS_PHASE_TIMING
+    if (threadIdx.x == 0 && blockIdx.x == 0) { bool any = false; for (int g = 0; g < a.NG; g++) any |= s.gflag[g] != 0; if (any) atomicAdd(&g_phase_cycles[20], 1ull); }
+#endif
 }
 
 template <typename T> __device__ __forceinline__ HybSm<T> hyb_carve(const HybArgs<T>& a, unsigned char* raw, bool adj, T*& extra) {
@@ -496,6 +561,8 @@ template <typename T> __device__ __forceinline__ HybSm<T> hyb_carve(const HybArg
     T* q = reinterpret_cast<T*>(raw);
     const int NC = a.n.NC;
     s.st[0] = q; q += 4 * NC; s.st[1] = q; q += 4 * NC;
+    s.ab = s.st[1];
+    if (adj) q += 4 * (size_t)(a.n.L - a.ML);      // 4 NI = 4 NC + 4 (macro lanes)
     s.own[0] = q; q += 2 * a.n.n_own; s.own[1] = q; q += 2 * a.n.n_own;
     s.aux[0] = q; q += a.ax.AUX; s.aux[1] = q; q += a.ax.AUX;
     s.fsig = q; q += 2 * a.ML; s.kconst = q; q += a.ML; s.headd = q; q += 2 * a.ML;
@@ -504,13 +571,25 @@ template <typename T> __device__ __forceinline__ HybSm<T> hyb_carve(const HybArg
         s.mid = q; q += 3 * NC;
         s.log.et = q; q += (size_t)a.NGL * (3 + a.MAXT);
     }
-    s.order = reinterpret_cast<int*>(q); q += ((size_t)a.n.L * sizeof(int) + sizeof(T) - 1) / sizeof(T);
+    {
+        const int NI = NC + (a.n.L - a.ML);
+        s.gh = q; q += 4 * (size_t)a.n.L;
+        s.flux = q; q += 2 * (size_t)NI;
+        unsigned char* pp = reinterpret_cast<unsigned char*>(q);
+        s.tb = net_tabs_carve<T>(pp, a.n, NI);
+        s.sd.s = nullptr;
+        if (adj && a.prefetch) s.sd = side_tab_carve<T>(pp, a.n.L);
+        q = reinterpret_cast<T*>(pp);
+    }
     s.walk = reinterpret_cast<int*>(q); q += ((size_t)a.NGL * 6 * sizeof(int) + sizeof(T) - 1) / sizeof(T);
     s.goff = reinterpret_cast<int*>(q); q += ((size_t)(a.NG + 1) * sizeof(int) + sizeof(T) - 1) / sizeof(T);
     s.walkT = q; q += a.NGL;
     s.par = reinterpret_cast<IdmPar<T>*>(q); q += ((size_t)a.NP * sizeof(IdmPar<T>) + sizeof(T) - 1) / sizeof(T);
     s.srcf = reinterpret_cast<int*>(q); q += ((size_t)2 * a.ML * sizeof(int) + sizeof(T) - 1) / sizeof(T);
     s.srcs = s.srcf + a.ML;
+    s.gflag = reinterpret_cast<int*>(q); q += ((size_t)(a.NG + a.NGL) * sizeof(int) + sizeof(T) - 1) / sizeof(T);
+    s.gof = s.gflag + a.NG;
+    s.hrec = reinterpret_cast<HeadRec<T>*>(q); q += ((size_t)a.ML * sizeof(HeadRec<T>) + sizeof(T) - 1) / sizeof(T);
     extra = q;
     return s;
 }
@@ -528,7 +607,7 @@ __global__ void __launch_bounds__(HYB_THREADS_MAX) hyb_rollout_fwd_kernel(HybArg
     extern __shared__ __align__(16) unsigned char raw[];
     T* extra;
     const HybSm<T> s = hyb_carve(a, raw, false, extra);
-    hyb_lane_order(a, s.order, s.par);
+    hyb_init(a, s);
     const int NC = a.n.NC, AUX = a.ax.AUX, n_own = a.n.n_own;
     unsigned fl = 0; int ncol = 0;
     for (int b = blockIdx.x; b < a.n.R; b += gridDim.x) {
@@ -554,7 +633,8 @@ __global__ void __launch_bounds__(HYB_THREADS_MAX) hyb_rollout_fwd_kernel(HybArg
                 for (int c = threadIdx.x; c < AUX; c += blockDim.x) ah[c] = s.aux[p][c];
             }
             if (t == a.n.T_steps) break;
-            hyb_step<T, false>(a, s, b, t, p, fl, ncol);
+            const StepRows<T> rows = global_rows(a.n, b, t);
+            hyb_step<T, false>(a, s, b, t, p, rows, fl, ncol);
             if (headh) {
                 T* hh = headh + ((size_t)t * a.n.R + b) * 2 * a.ML;
                 for (int c = threadIdx.x; c < 2 * a.ML; c += blockDim.x) hh[c] = s.headd[c];
@@ -572,7 +652,8 @@ __global__ void __launch_bounds__(HYB_THREADS_MAX) hyb_rollout_fwd_kernel(HybArg
 // dLoss/d(p, v, a) of the vehicles AFTER step t, by slot (other entries of the row are ignored).
 // outputs: g_r0, g_y0, g_u0 [R][NC]; g_own0 [R][n_own][2]; g_sig, g_inc [R][T][L]; g_aux0 [R][AUX] (p, v, a and
 // capacitor entries; the rest zero).
-// TMAX: largest CTA this instantiation is launched with.  Networks of up to 192 lanes (ITSCP 3 x 3: 144) get the
+// TMAX: largest CTA this instantiation is launched with: 192 threads (at least two CTAs per SM) or 512 (128 registers; the
+// kernel needs 106 since the macro lanes run interface-parallel).  Was: networks of up to 192 lanes (ITSCP 3 x 3: 144) get the
 // 170-register budget of two CTAs per SM; larger ones the full register file.
 template <typename T, int TMAX>
 __global__ void __launch_bounds__(TMAX, TMAX <= 192 ? 2 : 1) hyb_rollout_bwd_kernel(HybArgs<T> a, const T* __restrict__ hist, const T* __restrict__ ownh,
@@ -585,7 +666,7 @@ __global__ void __launch_bounds__(TMAX, TMAX <= 192 ? 2 : 1) hyb_rollout_bwd_ker
     extern __shared__ __align__(16) unsigned char raw[];
     T* q;
     HybSm<T> s = hyb_carve(a, raw, true, q);
-    hyb_lane_order(a, s.order, s.par);
+    hyb_init(a, s);
     const NetArgs<T>& n = a.n;
     const AuxL& x = a.ax;
     const int NC = n.NC, L = n.L, AUX = x.AUX, n_own = n.n_own, ML = a.ML, cap = a.cap;
@@ -595,14 +676,14 @@ __global__ void __launch_bounds__(TMAX, TMAX <= 192 ? 2 : 1) hyb_rollout_bwd_ker
     T* GC = q; q += a.NCAP;                    // adjoint of the flux capacitors
     // prefetch targets: the stored rows of step t - 1 stream in with cp.async while step t is processed; the buffers
     // rotate with s.st[0] / s.own[0] / s.aux[0] (no copy)
-    T* pre_st = q; q += 4 * NC;
-    T* pre_own = q; q += 2 * n_own;
-    T* pre_aux = q; q += AUX;
+    // (without a.prefetch -- networks whose buffers would not fit twice -- the rows are loaded at the top of their step)
+    T* pre_st = s.st[0]; T* pre_own = s.own[0]; T* pre_aux = s.aux[0];
+    if (a.prefetch) { pre_st = q; q += 4 * NC; pre_own = q; q += 2 * n_own; pre_aux = q; q += AUX; }
     T* pub = q; q += (size_t)L * 6;            // [L][2 sides][3] published (d green r, d green u, d signal)
     T* pubm = q; q += (size_t)ML * 5;          // [ML] (d signal prev, curr, next, d leader p, d leader v)
     int* pubi = reinterpret_cast<int*>(q);     // [ML][4] prev lane, next lane, leader micro index, leader slot
     s.log.ei = pubi + 4 * ML;                  // [NGL][4]
-    const T inv_umax = T(1) / n.umax, inv15 = T(1) / (T(1.5) * n.umax), inv_dt = T(1) / n.dt;
+    const T inv_dt = T(1) / n.dt;
     const T vlen = a.vlen;
     bool nan = false;
     unsigned fl = 0; int ncol = 0;
@@ -632,22 +713,43 @@ __global__ void __launch_bounds__(TMAX, TMAX <= 192 ? 2 : 1) hyb_rollout_bwd_ker
             for (int c = threadIdx.x; c < AUX; c += blockDim.x) __pipeline_memcpy_async(pre_aux + c, ah_ + c, sizeof(T)); \
             __pipeline_commit();                                                                                       \
         }
-        if (n.T_steps > 0) DHTS_HYB_PREFETCH(n.T_steps - 1)
+        if (n.T_steps > 0 && a.prefetch) DHTS_HYB_PREFETCH(n.T_steps - 1)
+        DHTS_PT_DECL
         for (int t = n.T_steps - 1; t >= 0; t--) {
-            __pipeline_wait_prior(0);
-            __syncthreads();          // rows of step t have landed; the previous step's last readers of s.st[0] are done
-            { T* x_ = s.st[0]; s.st[0] = pre_st; pre_st = x_; x_ = s.own[0]; s.own[0] = pre_own; pre_own = x_;
-              x_ = s.aux[0]; s.aux[0] = pre_aux; pre_aux = x_; }
-            if (t > 0) DHTS_HYB_PREFETCH(t - 1)
+            DHTS_PT(15)     // gathers of the previous step
+            if (a.prefetch) {
+                __pipeline_wait_prior(0);
+                __syncthreads();          // rows of step t have landed; the previous step's last readers of s.st[0] are done
+                { T* x_ = s.st[0]; s.st[0] = pre_st; pre_st = x_; x_ = s.own[0]; s.own[0] = pre_own; pre_own = x_;
+                  x_ = s.aux[0]; s.aux[0] = pre_aux; pre_aux = x_; }
+                if (t > 0) DHTS_HYB_PREFETCH(t - 1)
+            } else {
+                __syncthreads();          // the previous step's last readers of s.st[0] are done
+                DHTS_HYB_PREFETCH(t)
+                __pipeline_wait_prior(0);
+                __syncthreads();
+            }
 #undef DHTS_HYB_PREFETCH
-            hyb_step<T, true>(a, s, b, t, 0, fl, ncol);          // replay: s.mid, s.log, s.kconst, s.aux[1]
+            DHTS_PT(10)     // rows landed
+            const StepRows<T> rows = global_rows(n, b, t);
+            hyb_step<T, true>(a, s, b, t, 0, rows, fl, ncol);    // replay: s.mid, s.log, s.kconst, s.aux[1]
+            DHTS_PT(11)     // replay (its phases: 0-5)
             const T* cr = s.st[0]; const T* cy = cr + NC; const T* cu = cy + NC; const T* ce = cu + NC;
             const T* auxc = s.aux[0];
-            const int* rt = n.route ? n.route + (size_t)b * n.route_stride + (size_t)t * 2 * L : nullptr;
-            const T* sig_t = n.sig ? n.sig + ((size_t)b * n.T_steps + t) * L : nullptr;
-            const T* inc_t = n.incoming ? n.incoming + ((size_t)b * n.T_steps + t) * L : nullptr;
-            // ---- R1: conversions reversed, last lane of each group first
+            const int* rt = rows.rt; const T* sig_t = rows.sig; const T* inc_t = rows.inc;
+            // ---- R1: conversions reversed.  Groups without an event other than the capacitors' flux (s.gflag of the replay):
+            // one thread per group lane; the others: one thread per group, last lane first
+            for (int gi = threadIdx.x; gi < a.NGL; gi += blockDim.x) {
+                if (s.gflag[s.gof[gi]]) continue;
+                const int* e = s.log.ei + gi * 4;
+                if (e[0] != EV_CAP) continue;
+                const int k = e[2], c = s.walk[gi * 6 + 5];
+                const T* et = s.log.et + gi * (3 + a.MAXT);
+                const T gf = GC[k];
+                G[c] += gf * et[1] * n.dt; G[2 * NC + c] += gf * et[0] * n.dt;
+            }
             for (int g = threadIdx.x; g < a.NG; g += blockDim.x) {
+                if (!s.gflag[g]) continue;
                 for (int gi = s.goff[g + 1] - 1; gi >= s.goff[g]; gi--) {
                     const int* e = s.log.ei + gi * 4;
                     const int ev = e[0];
@@ -694,76 +796,33 @@ __global__ void __launch_bounds__(TMAX, TMAX <= 192 ? 2 : 1) hyb_rollout_bwd_ker
                 }
             }
             __syncthreads();
-            // ---- R2: every lane's operator reversed
+            DHTS_PT(12)     // R1
+            // ---- R2: every lane's operator reversed.  Macro lanes in three sub-phases (dhts_net_if.cuh); the micro lanes, one
+            // thread each from the far end of the CTA, run beside the first one.
             bool dummy = false;
-            for (int li = threadIdx.x; li < L; li += blockDim.x) {
-                const int l = s.order[li];
-                if (n.kind[l] == 0) {
-                    const int c0 = n.cell_off[l], N = n.cell_off[l + 1] - c0;
-                    const T dxl = n.dx[l], cc = n.dt / dxl;
-                    for (int i = 0; i < N; i++) {       // nu = compute_u(nr, ny): true derivative, at the state before conversions
-                        T dr, dy; du_dry(s.mid[c0 + i], s.mid[NC + c0 + i], n.umax, dr, dy);
-                        const T gu = G[2 * NC + c0 + i];
-                        G[c0 + i] += gu * dr; G[NC + c0 + i] += gu * dy;
-                    }
-                    const Side<T> sl = resolve_side(n, l, 0, rt, cr, cu, s.own[0], sig_t, inc_t, dummy);
-                    const Side<T> sr = resolve_side(n, l, 1, rt, cr, cu, s.own[0], sig_t, inc_t, dummy);
-                    const Cell<T> gL = ghost_cell<T, true>(sl.fr, sl.fu, n.umax);
-                    const Cell<T> gR = ghost_cell<T, true>(sr.fr, sr.fu, n.umax);
-                    Cell<T> Lc = gL;
-                    T gLr = T(0), gLy = T(0), pbr = T(0), pby = T(0);
-                    T ggl_r = T(0), ggl_y = T(0), ggr_r = T(0), ggr_y = T(0);
-                    for (int i = 0; i <= N; i++) {
-                        const Cell<T> Rc = (i < N) ? derive_cell_stored<T, true>(cr[c0 + i], cy[c0 + i], cu[c0 + i], ce[c0 + i], true, n.umax) : gR;
-                        const T gRr = (i < N) ? G[c0 + i] : T(0), gRy = (i < N) ? G[NC + c0 + i] : T(0);
-                        const Riem<T> o = riemann(Lc, Rc, n.umax, inv_umax, inv15, n.dt, dxl);
-                        T par, pay, qbr, qby;
-                        riemann_adj(Lc, Rc, o, n.umax, inv_umax, inv15, gRr - gLr, gRy - gLy, par, pay, qbr, qby);
-                        if (i == 0) { ggl_r = cc * par; ggl_y = cc * pay; }
-                        else {
-                            const T nr_ = gLr + cc * (par + pbr), ny_ = gLy + cc * (pay + pby);
-                            nan |= t_isnan(nr_) || t_isnan(ny_);
-                            G[c0 + i - 1] = nr_; G[NC + c0 + i - 1] = ny_;
-                        }
-                        if (i == N) { ggr_r = cc * qbr; ggr_y = cc * qby; }
-                        pbr = qbr; pby = qby; gLr = gRr; gLy = gRy; Lc = Rc;
-                    }
-                    for (int i = 0; i < N; i++) G[2 * NC + c0 + i] = T(0);
-                    for (int side = 0; side < 2; side++) {
-                        const Side<T>& sd = side == 0 ? sl : sr;
-                        const T g_r = side == 0 ? ggl_r : ggr_r, g_y = side == 0 ? ggl_y : ggr_y;
-                        const T ue = u_eq(sd.fr, n.umax);
-                        T gfr = g_r + g_y * (sd.fu - ue - sd.fr * u_eq_true_prime(sd.fr, n.umax));
-                        T gfu = g_y * sd.fr;
-                        const int os = n.own_slot[side * L + l];
-                        if (os >= 0) { gfr += GO[2 * os]; gfu += GO[2 * os + 1]; }
-                        T ggr = gfr, ggu = gfu, gs = T(0);
-                        if (n.mode == 1) {
-                            const T red_r = side == 0 ? T(0) : T(1), red_u = side == 0 ? n.umax : T(0);
-                            ggr = gfr * sd.s; ggu = gfu * sd.s;
-                            gs = gfr * (sd.gr_ - red_r) + gfu * (sd.gu_ - red_u);
-                            if (side == 1) gs = n.soft ? gs * T(32) * sd.s * (T(1) - sd.s) : T(0);
-                            if (sd.sig_lane < 0) gs = T(0);
-                        }
-                        if (os >= 0) {
-                            const bool own_src = sd.src == -1;
-                            GO[2 * os] = own_src ? ggr : T(0); GO[2 * os + 1] = own_src ? ggu : T(0);
-                        }
-                        if (sd.src == -2 && g_inc)
-                            g_inc[((size_t)b * n.T_steps + t) * L + l] = ggr + ggu * u_eq_true_prime(sd.gr_, n.umax);
-                        T* pb = pub + ((size_t)l * 2 + side) * 3;
-                        pb[0] = sd.src >= 0 ? ggr : T(0); pb[1] = sd.src >= 0 ? ggu : T(0); pb[2] = gs;
-                    }
-                    if (g_inc && !(n.mode == 1 && n.nadj[l] == 0)) g_inc[((size_t)b * n.T_steps + t) * L + l] = T(0);
-                } else {
-                    const int m = a.mic_of[l];
+            T* g_inc_row = g_inc ? g_inc + ((size_t)b * n.T_steps + t) * L : nullptr;
+            for (int c = threadIdx.x; c < NC; c += blockDim.x) {      // nu = compute_u(nr, ny): true derivative, at the state before conversions
+                T dr, dy; du_dry(s.mid[c], s.mid[NC + c], n.umax, dr, dy);
+                const T gu = G[2 * NC + c];
+                G[c] += gu * dr; G[NC + c] += gu * dy;
+            }
+            for (int q = threadIdx.x; q < 2 * L; q += blockDim.x) {
+                const int side = q >= L, l = q - side * L;
+                if (n.kind[l]) continue;
+                const Side<T> sv = resolve_side(n, l, side, rt, cr, cu, s.own[0], sig_t, inc_t, dummy);
+                s.gh[2 * q] = sv.fr; s.gh[2 * q + 1] = sv.fu;
+                if (s.sd.s) { s.sd.src[q] = sv.src; s.sd.sig_lane[q] = sv.sig_lane; s.sd.s[q] = sv.s; s.sd.gr[q] = sv.gr_; s.sd.gu[q] = sv.gu_; }
+            }
+            for (int m = (int)blockDim.x - 1 - (int)threadIdx.x; m < ML; m += blockDim.x) {
+                const int l = a.mic_lane[m];
+                {
                     const int f = (int)auxc[x.FRONT + m], cnt = (int)auxc[x.CNT + m];
                     T* pm = pubm + m * 5; int* pi = pubi + m * 4;
                     pm[0] = pm[1] = pm[2] = pm[3] = pm[4] = T(0); pi[0] = pi[1] = pi[2] = -1; pi[3] = 0;
                     for (int k = 0; k < 6; k++) pub[(size_t)l * 6 + k] = T(0);
                     if (g_inc) g_inc[((size_t)b * n.T_steps + t) * L + l] = T(0);
                     if (cnt > 0) {
-                        const HeadRec<T> h = head_rec(a, l, m, auxc, sig_t);
+                        const HeadRec<T>& h = s.hrec[m];                     // of the replayed step
                         const T dp = s.headd[2 * m], dv = s.headd[2 * m + 1];
                         T pl = T(0), vl = T(0), g_dp = T(0), g_dv = T(0);
                         int oprev = 0;
@@ -811,46 +870,79 @@ __global__ void __launch_bounds__(TMAX, TMAX <= 192 ? 2 : 1) hyb_rollout_bwd_ker
                 }
             }
             __syncthreads();
-            // ---- R3: gathers (edge cells and signals the neighbours used, leaders of other lanes' heads), injections
-            for (int l = threadIdx.x; l < L; l += blockDim.x) {
-                T gsig = T(0);
-                for (int m2 = 0; m2 < ML; m2++) {
-                    const T* pm = pubm + m2 * 5; const int* pi = pubi + m2 * 4;
-                    if (pi[0] == l) gsig += pm[0];
-                    if (a.mic_lane[m2] == l) gsig += pm[1];
-                    if (pi[1] == l) gsig += pm[2];
+            DHTS_PT(13)     // R2a: fold, ghosts, micro lanes
+            net_adj_flux<T>(n, s.tb, cr, cy, cu, ce, s.gh, G, G + NC, s.ab);
+            __syncthreads();
+            DHTS_PT(14)     // R2b: interfaces
+            for (int c = threadIdx.x; c < NC; c += blockDim.x) {
+                const int l = s.tb.lane_of_cell[c];
+                const int it = s.tb.if_off[l] + (c - n.cell_off[l]);      // interface on the cell's left; it + 1 on its right
+                const T cc = s.tb.cc[l];
+                const T nr_ = fma(cc, s.ab[4 * (it + 1)] + s.ab[4 * it + 2], G[c]);
+                const T ny_ = fma(cc, s.ab[4 * (it + 1) + 1] + s.ab[4 * it + 3], G[NC + c]);
+                nan |= t_isnan(nr_) || t_isnan(ny_);
+                T nu_ = T(0);                                              // the stored speed of state t: filled by the gathers
+                if (g_states && t > 0) {                                   // injected adjoint of state t (the state after step t - 1)
+                    const T* gs_ = g_states + ((size_t)(t - 1) * n.R + b) * 4 * NC;
+                    G[c] = nr_ + gs_[c]; G[NC + c] = ny_ + gs_[NC + c]; nu_ = gs_[2 * NC + c];
+                } else { G[c] = nr_; G[NC + c] = ny_; }
+                G[2 * NC + c] = nu_;
+            }
+            for (int q = threadIdx.x; q < 2 * L; q += blockDim.x) {
+                const int side = q >= L, l = q - side * L;
+                if (n.kind[l]) continue;
+                const T cc = s.tb.cc[l];
+                const T* o = s.ab + 4 * (size_t)(side == 0 ? s.tb.if_off[l] : s.tb.if_off[l + 1] - 1);
+                const T g_r = cc * (side == 0 ? o[0] : o[2]), g_y = cc * (side == 0 ? o[1] : o[3]);
+                if (s.sd.s)
+                    net_adj_side<T>(n, s.gh, l, side, s.sd.src[q], s.sd.sig_lane[q], s.sd.s[q], s.sd.gr[q], s.sd.gu[q], g_r, g_y, GO, pub,
+                                    g_inc_row);
+                else {      // lean shared-memory mode: the side record is resolved again
+                    const Side<T> sv = resolve_side(n, l, side, rt, cr, cu, s.own[0], sig_t, inc_t, dummy);
+                    net_adj_side<T>(n, s.gh, l, side, sv.src, sv.sig_lane, sv.s, sv.gr_, sv.gu_, g_r, g_y, GO, pub, g_inc_row);
                 }
-                if (n.kind[l] == 0) {
-                    const int c0 = n.cell_off[l], N = n.cell_off[l + 1] - c0;
-                    gsig += pub[((size_t)l * 2 + 1) * 3 + 2];
-                    for (int e = n.adj_off[(L + 1) + l]; e < n.adj_off[(L + 1) + l + 1]; e++) {
-                        const int nn = n.adj[e];
-                        if (n.kind[nn]) continue;
-                        const int cnt = n.nadj[nn];
-                        const int sel = rt ? rt[nn] : -1;
-                        const int srcn = cnt == 1 ? n.one_adj[nn] : (cnt > 1 ? sel : -1);
-                        const T* pb = pub + ((size_t)nn * 2 + 0) * 3;
-                        if (srcn == l) { G[c0 + N - 1] += pb[0]; G[2 * NC + c0 + N - 1] += pb[1]; }
-                        if (n.mode == 1 && sel == l) gsig += pb[2];
+            }
+            __syncthreads();
+            DHTS_PT(16)     // R2c: cells, sides
+            // ---- R3: gathers (edge cells and signals the neighbours used, leaders of other lanes' heads), injected vehicle adjoints.
+            // A micro lane's head blends the signals of its own lane and of the lanes before / after it on its route -- neighbours
+            // in the lane graph -- so every lane collects those terms while it walks its adjacency lists.
+            for (int l = threadIdx.x; l < L; l += blockDim.x) {
+                const bool mac = n.kind[l] == 0;
+                const int c0 = n.cell_off[l], N = n.cell_off[l + 1] - c0;
+                T gsig = mac ? pub[((size_t)l * 2 + 1) * 3 + 2] : pubm[a.mic_of[l] * 5 + 1];
+                for (int e = n.adj_off[(L + 1) + l]; e < n.adj_off[(L + 1) + l + 1]; e++) {      // successors
+                    const int nn = n.adj[e];
+                    if (n.kind[nn]) {                      // its head came from lane l: d (signal of the previous lane)
+                        const int m2 = a.mic_of[nn];
+                        if (pubi[m2 * 4] == l) gsig += pubm[m2 * 5];
+                        continue;
                     }
-                    for (int e = n.adj_off[l]; e < n.adj_off[l + 1]; e++) {
-                        const int pl = n.adj[e];
-                        if (n.kind[pl]) continue;
-                        const int cnt = n.nadj[L + pl];
-                        const int sel = rt ? rt[L + pl] : -1;
-                        const int srcp = cnt == 1 ? n.one_adj[L + pl] : (cnt > 1 ? sel : -1);
-                        const T* pb = pub + ((size_t)pl * 2 + 1) * 3;
-                        if (srcp == l) { G[c0] += pb[0]; G[2 * NC + c0] += pb[1]; }
+                    if (!mac) continue;
+                    const int cnt = n.nadj[nn];
+                    const int sel = rt ? rt[nn] : -1;
+                    const int srcn = cnt == 1 ? n.one_adj[nn] : (cnt > 1 ? sel : -1);
+                    const T* pb = pub + ((size_t)nn * 2 + 0) * 3;
+                    if (srcn == l) { G[c0 + N - 1] += pb[0]; G[2 * NC + c0 + N - 1] += pb[1]; }
+                    if (n.mode == 1 && sel == l) gsig += pb[2];
+                }
+                for (int e = n.adj_off[l]; e < n.adj_off[l + 1]; e++) {                          // predecessors
+                    const int pl = n.adj[e];
+                    if (n.kind[pl]) {                      // its head goes on to lane l: d (signal of the next lane)
+                        const int m2 = a.mic_of[pl];
+                        if (pubi[m2 * 4 + 1] == l) gsig += pubm[m2 * 5 + 2];
+                        continue;
                     }
-                    if (g_states && t > 0) {
-                        const T* gs_ = g_states + ((size_t)(t - 1) * n.R + b) * 4 * NC;
-                        for (int i = 0; i < N; i++) {
-                            G[c0 + i] += gs_[c0 + i]; G[NC + c0 + i] += gs_[NC + c0 + i]; G[2 * NC + c0 + i] += gs_[2 * NC + c0 + i];
-                        }
-                    }
-                } else {
+                    if (!mac) continue;
+                    const int cnt = n.nadj[L + pl];
+                    const int sel = rt ? rt[L + pl] : -1;
+                    const int srcp = cnt == 1 ? n.one_adj[L + pl] : (cnt > 1 ? sel : -1);
+                    const T* pb = pub + ((size_t)pl * 2 + 1) * 3;
+                    if (srcp == l) { G[c0] += pb[0]; G[2 * NC + c0] += pb[1]; }
+                }
+                if (!mac) {
                     const int m = a.mic_of[l];
-                    for (int m2 = 0; m2 < ML; m2++) {
+                    for (int m2 = 0; m2 < ML; m2++) {      // heads whose leader is a vehicle of this lane (possibly lanes ahead of them)
                         const int* pi = pubi + m2 * 4;
                         if (pi[2] == m) { GV[m * cap + pi[3]] += pubm[m2 * 5 + 3]; GV[ML * cap + m * cap + pi[3]] += pubm[m2 * 5 + 4]; }
                     }
@@ -901,7 +993,15 @@ static int hyb_sm_count() {
     }
     return nsm;
 }
-static int hyb_threads(int L) { int t = (L + 31) / 32 * 32; return t > HYB_THREADS_MAX ? HYB_THREADS_MAX : (t < 32 ? 32 : t); }
+// Few replicas (a CTA's step time is what counts): one thread per interface of the macro lanes, and at least one per (side,
+// lane) plus one per micro lane.  Many replicas (several CTAs per SM hide each other's barriers): half as many, looping.
+template <typename T> static int hyb_threads(const HybArgs<T>& a) {
+    const int NI = a.n.NC + (a.n.L - a.ML), sides = 2 * a.n.L + a.ML;
+    int w = NI > sides ? NI : sides;
+    if (a.n.R > hyb_sm_count()) w = (w + 1) / 2;
+    int t = (w + 31) / 32 * 32;
+    return t > HYB_THREADS_MAX ? HYB_THREADS_MAX : (t < 32 ? 32 : t);
+}
 
 template <typename T> static size_t hyb_smem(const HybArgs<T>& a, bool adj) {
     const size_t NC = a.n.NC, L = a.n.L, ML = a.ML;
@@ -910,14 +1010,20 @@ template <typename T> static size_t hyb_smem(const HybArgs<T>& a, bool adj) {
     if (adj) {
         el += 3 * NC + (size_t)a.NGL * (3 + a.MAXT);                       // mid, log.et
         el += 3 * NC + 2 * (size_t)a.n.n_own + 3 * ML * a.cap + a.NCAP + 6 * L + 5 * ML;
-        el += 4 * NC + 2 * (size_t)a.n.n_own + (size_t)a.ax.AUX;               // prefetch targets
+        if (a.prefetch) el += 4 * NC + 2 * (size_t)a.n.n_own + (size_t)a.ax.AUX;   // prefetch targets
         bytes += sizeof(int) * (4 * ML + 4 * (size_t)a.NGL);
     }
-    bytes += sizeof(int) * L + sizeof(T);                                  // order
+    {
+        const size_t NI = NC + (L - ML);
+        el += 4 * L + 2 * NI + (adj ? 4 * (L - ML) : 0);                    // gh, flux, tail of (A^T w, B^T w) behind st[1]
+        bytes += net_tabs_bytes<T>((int)L, (int)NC, (int)NI) + (adj && a.prefetch ? side_tab_bytes<T>((int)L) : 0);
+    }
     bytes += sizeof(int) * 6 * (size_t)a.NGL + sizeof(T);                  // walk
     bytes += sizeof(int) * (size_t)(a.NG + 1) + sizeof(T); el += a.NGL;   // goff, walkT
     bytes += sizeof(IdmPar<T>) * (size_t)a.NP + sizeof(T);                // par
     bytes += sizeof(int) * 2 * ML + sizeof(T);                            // srcf, srcs
+    bytes += sizeof(int) * (size_t)(a.NG + a.NGL) + sizeof(T);            // gflag, gof
+    bytes += sizeof(HeadRec<T>) * ML + sizeof(T);                         // hrec
     return sizeof(T) * el + bytes + 32;
 }
 
@@ -967,6 +1073,7 @@ static HybArgs<T> hyb_args(const dhts_hyb_topology* tp, const T* dx, const T* la
     a.grp_off = tp->grp_off; a.grp_lane = tp->grp_lane; a.routes = tp->routes; a.lane_len = lane_len;
     a.spawn_route = spawn_route; a.spawn_stride = spawn_per_replica ? (long long)tp->ML * KS : 0;
     a.par_tab = veh_par; a.NP = n_par; a.vlen = veh_len;
+    a.prefetch = 1;
     a.src = tp->src; a.rnd = src_rand; a.NRAND = n_rand; a.rnd_stride = rand_per_replica ? (long long)n_rand : 0;
     a.head_dp0 = T(1000); a.head_dv0 = T(0);
     a.ax = aux_layout(tp->ML, tp->cap, tp->NCAP);
@@ -994,7 +1101,7 @@ static HybArgs<T> hyb_args(const dhts_hyb_topology* tp, const T* dx, const T* la
         if (rc) return rc;                                                                                             \
         if (a.n.n_own > 0 && (!own0 || !own_hist)) return DHTS_ERR_INVALID;                                            \
         if (R == 0) return DHTS_OK;                                                                                    \
-        const int threads = dhts::hyb_threads(a.n.L);                                                                  \
+        const int threads = dhts::hyb_threads(a);                                                                  \
         const size_t smem = dhts::hyb_smem<T>(a, false);                                                               \
         int grid = 1;                                                                                                  \
         rc = dhts::hyb_launch_cfg(dhts::hyb_rollout_fwd_kernel<T>, smem, threads, R, &grid);                           \
@@ -1023,8 +1130,9 @@ static HybArgs<T> hyb_args(const dhts_hyb_topology* tp, const T* dx, const T* la
         if (rc) return rc;                                                                                             \
         if (a.n.n_own > 0 && !own_hist) return DHTS_ERR_INVALID;                                                       \
         if (R == 0) return DHTS_OK;                                                                                    \
-        const int threads = dhts::hyb_threads(a.n.L);                                                                  \
-        const size_t smem = dhts::hyb_smem<T>(a, true);                                                                \
+        const int threads = dhts::hyb_threads(a);                                                                  \
+        size_t smem = dhts::hyb_smem<T>(a, true);                                                                      \
+        if (smem > 227 * 1024) { a.prefetch = 0; smem = dhts::hyb_smem<T>(a, true); }                                  \
         int grid = 1;                                                                                                  \
         if (threads <= 192) {                                                                                          \
             rc = dhts::hyb_launch_cfg(dhts::hyb_rollout_bwd_kernel<T, 192>, smem, threads, R, &grid);                  \

@@ -31,43 +31,42 @@
 // blend, and publishes (d green, d signal) per side in shared memory; after one barrier each lane GATHERS what its
 // neighbours published for its edge cells and for its signal (fixed order: deterministic, no atomics).
 #include <cuda_pipeline.h>
-#include "dhts_net.cuh"
+#include "dhts_net_if.cuh"
 
 namespace dhts {
 
-// Thread -> lane assignment: lanes sorted by their number of cells (stable), so that the threads of a warp sweep lanes
-// of equal length (an ITSCP grid mixes 1-, 2- and 4-cell lanes: in lane-id order a warp ran at 56 % thread efficiency,
-// profiles/r1n_net_ncu_summary.json).  order[rank] = lane; every thread calls it; ends with a block barrier.
-template <typename T> __device__ __forceinline__ void lane_order(const NetArgs<T>& a, int* order) {
-    for (int l = threadIdx.x; l < a.L; l += blockDim.x) {
-        const int n = a.cell_off[l + 1] - a.cell_off[l];
-        int rank = 0;
-        for (int j = 0; j < a.L; j++) {
-            const int m = a.cell_off[j + 1] - a.cell_off[j];
-            rank += (m > n) || (m == n && j < l);
-        }
-        order[rank] = l;
-    }
-    __syncthreads();
+// Shared-memory layout (host and device agree through these two functions).
+//   forward:  tabs | state x 2 (r, y, u) | own x 2 | gh [2][L][2] | flux [NI][2] | qc [NC] | red [threads]
+//   adjoint:  tabs | side tab | cur, nxt, pre (r, y, u) | G (gr, gy, gu) | own, own_pre, GO | gh | ab [NI][4] | pub [L][2][3] | gq [L]
+template <typename T> static size_t net_smem(int L, int NC, int n_own, bool adj, int threads) {
+    const int NI = NC + L;
+    size_t b = net_tabs_bytes<T>(L, NC, NI);
+    if (!adj) return b + sizeof(T) * ((size_t)6 * NC + 4 * n_own + 4 * (size_t)L + 2 * (size_t)NI + NC + threads) + 16;
+    return b + side_tab_bytes<T>(L) +
+           sizeof(T) * ((size_t)12 * NC + 6 * n_own + 4 * (size_t)L + 4 * (size_t)NI + 6 * (size_t)L + NC) + 16;
 }
 
 // ------------------------------------------------------------------------------------------------ forward
 // hist  [T+1][R][3][NC]  state (r, y, u) before step t (t = 0..T-1) and after the last step
 // ownh  [T+1][R][n_own][2] carried own-ghost records, same indexing
 template <typename T>
-__global__ void __launch_bounds__(256) net_rollout_fwd_kernel(NetArgs<T> a, const T* __restrict__ r0, const T* __restrict__ y0,
+__global__ void __launch_bounds__(512) net_rollout_fwd_kernel(NetArgs<T> a, const T* __restrict__ r0, const T* __restrict__ y0,
                                                                const T* __restrict__ u0, const T* __restrict__ own0,
                                                                T* __restrict__ hist, T* __restrict__ ownh,
                                                                T* __restrict__ reward, int* __restrict__ flags) {
     extern __shared__ __align__(16) unsigned char raw[];
-    T* sm = reinterpret_cast<T*>(raw);
-    const int NC = a.NC, L = a.L;
+    const int NC = a.NC, L = a.L, NI = NC + L;
+    unsigned char* pp = raw;
+    const NetTabs<T> tb = net_tabs_carve<T>(pp, a, NI);
+    T* sm = reinterpret_cast<T*>(pp);
     T* buf[2] = {sm, sm + 3 * NC};                         // (r, y, u) x NC, double buffered
     T* own[2] = {sm + 6 * NC, sm + 6 * NC + 2 * a.n_own};
-    T* red = sm + 6 * NC + 4 * a.n_own;                    // [blockDim] reward reduction
-    int* order = reinterpret_cast<int*>(red + blockDim.x);  // [L] lanes by decreasing number of cells
-    const T inv_umax = T(1) / a.umax, inv15 = T(1) / (T(1.5) * a.umax);
-    lane_order(a, order);
+    T* gh = sm + 6 * NC + 4 * a.n_own;                     // [2][L][2] final ghost (r, u) of the step
+    T* flux = gh + 4 * L;                                  // [NI][2]
+    T* qc = flux + 2 * NI;                                 // [NC] queue-reward terms of the cells
+    T* red = qc + NC;                                      // [blockDim] reward reduction
+    net_tabs_init(a, tb);
+    const T inv_veh_len = T(1) / a.veh_len;
     for (int b = blockIdx.x; b < a.R; b += gridDim.x) {
         __syncthreads();
         for (int c = threadIdx.x; c < NC; c += blockDim.x) {
@@ -78,53 +77,60 @@ __global__ void __launch_bounds__(256) net_rollout_fwd_kernel(NetArgs<T> a, cons
         bool bad = false, bad_route = false;
         T rew = T(0);
         int p = 0;
-        for (int t = 0; t <= a.T_steps; t++) {
+        // per-step rows of the inputs and of the stored history: advanced by one stride per step
+        const int* rt = a.route ? a.route + (size_t)b * a.route_stride : nullptr;
+        const T* sig_t = a.sig ? a.sig + (size_t)b * a.T_steps * L : nullptr;
+        const T* inc_t = a.incoming ? a.incoming + (size_t)b * a.T_steps * L : nullptr;
+        T* h = hist + (size_t)b * 3 * NC;
+        T* oh = ownh + (size_t)b * 2 * a.n_own;
+        const size_t h_stride = (size_t)a.R * 3 * NC, oh_stride = (size_t)a.R * 2 * a.n_own;
+        for (int t = 0; t <= a.T_steps; t++, h += h_stride, oh += oh_stride) {
             const T* cr = buf[p]; const T* cy = cr + NC; const T* cu = cy + NC;
-            {   // store the state before step t (coalesced)
-                T* h = hist + ((size_t)t * a.R + b) * 3 * NC;
-                for (int c = threadIdx.x; c < 3 * NC; c += blockDim.x) h[c] = cr[c];
-                T* oh = ownh + ((size_t)t * a.R + b) * 2 * a.n_own;
-                for (int c = threadIdx.x; c < 2 * a.n_own; c += blockDim.x) oh[c] = own[p][c];
+            // store the state before step t (coalesced)
+            for (int c = threadIdx.x; c < 3 * NC; c += blockDim.x) h[c] = cr[c];
+            for (int c = threadIdx.x; c < 2 * a.n_own; c += blockDim.x) oh[c] = own[p][c];
+            // queue reward of the state after step t - 1, lane by lane (its cell terms were left in qc)
+            if (a.qk && t > 0) {
+                for (int l = threadIdx.x; l < L; l += blockDim.x) {
+                    T q = T(0);
+                    for (int c = a.cell_off[l]; c < a.cell_off[l + 1]; c++) q += qc[c];
+                    rew -= q * q * a.dt;
+                }
             }
             if (t == a.T_steps) break;
             T* nr = buf[p ^ 1]; T* ny = nr + NC; T* nu = ny + NC;
-            const int* rt = a.route ? a.route + (size_t)b * a.route_stride + (size_t)t * 2 * L : nullptr;
-            const T* sig_t = a.sig ? a.sig + ((size_t)b * a.T_steps + t) * L : nullptr;
-            const T* inc_t = a.incoming ? a.incoming + ((size_t)b * a.T_steps + t) * L : nullptr;
-            for (int li = threadIdx.x; li < L; li += blockDim.x) {
-                const int l = order[li];
-                const int c0 = a.cell_off[l], N = a.cell_off[l + 1] - c0;
-                const T dxl = a.dx[l], cc = a.dt / dxl;
-                const Side<T> sl = resolve_side(a, l, 0, rt, cr, cu, own[p], sig_t, inc_t, bad_route);
-                const Side<T> sr = resolve_side(a, l, 1, rt, cr, cu, own[p], sig_t, inc_t, bad_route);
-                const int osl = a.own_slot[l], osr = a.own_slot[L + l];
-                if (osl >= 0) { own[p ^ 1][2 * osl] = sl.fr; own[p ^ 1][2 * osl + 1] = sl.fu; }
-                if (osr >= 0) { own[p ^ 1][2 * osr] = sr.fr; own[p ^ 1][2 * osr + 1] = sr.fu; }
-                Cell<T> Lc = ghost_cell<T, false>(sl.fr, sl.fu, a.umax);
-                T fpr = T(0), fpy = T(0), q = T(0);
-                for (int i = 0; i <= N; i++) {
-                    const Cell<T> Rc = (i < N) ? derive_cell_stored<T, false>(cr[c0 + i], cy[c0 + i], cu[c0 + i], T(0), false, a.umax)
-                                               : ghost_cell<T, false>(sr.fr, sr.fu, a.umax);
-                    const Riem<T> o = riemann(Lc, Rc, a.umax, inv_umax, inv15, a.dt, dxl);
-                    bad |= o.cfl_bad;
-                    const T fr = o.r0 * o.u0, fy = o.y0 * o.u0;
-                    if (i > 0) {
-                        const T r = cr[c0 + i - 1] + (fpr - fr) * cc;
-                        const T y = cy[c0 + i - 1] + (fpy - fy) * cc;
-                        const T u = compute_u(r, y, a.umax);
-                        nr[c0 + i - 1] = r; ny[c0 + i - 1] = y; nu[c0 + i - 1] = u;
-                        if (a.qk) {
-                            T z = (a.static_speed - u) * a.qk[t];
-                            z = z < T(-16) ? T(-16) : (z > T(16) ? T(16) : z);
-                            q += sigm(z) * (r * dxl / a.veh_len);
-                        }
-                    }
-                    fpr = fr; fpy = fy; Lc = Rc;
+            // ---- G: ghosts, one thread per (side, lane)
+            for (int q = threadIdx.x; q < 2 * L; q += blockDim.x) {
+                const int side = q >= L, l = q - side * L;
+                const Side<T> sd = resolve_side(a, l, side, rt, cr, cu, own[p], sig_t, inc_t, bad_route);
+                gh[2 * q] = sd.fr; gh[2 * q + 1] = sd.fu;
+                const int os = a.own_slot[q];
+                if (os >= 0) { own[p ^ 1][2 * os] = sd.fr; own[p ^ 1][2 * os + 1] = sd.fu; }
+            }
+            __syncthreads();
+            // ---- I: fluxes, one thread per interface
+            bad |= net_fwd_flux<T>(a, tb, cr, cy, cu, nullptr, gh, flux);
+            __syncthreads();
+            // ---- C: update, one thread per cell (_macro_lane.py:83-114; set_r_y refreshes u, _arz.py:88-92)
+            for (int c = threadIdx.x; c < NC; c += blockDim.x) {
+                const int l = tb.lane_of_cell[c];
+                const int it = tb.if_off[l] + (c - a.cell_off[l]);
+                const T cc = tb.cc[l];
+                const T r = fma(flux[2 * it] - flux[2 * it + 2], cc, cr[c]);
+                const T y = fma(flux[2 * it + 1] - flux[2 * it + 3], cc, cy[c]);
+                const T u = compute_u(r, y, a.umax);
+                nr[c] = r; ny[c] = y; nu[c] = u;
+                if (a.qk) {
+                    T z = (a.static_speed - u) * a.qk[t];
+                    z = z < T(-16) ? T(-16) : (z > T(16) ? T(16) : z);
+                    qc[c] = sigm(z) * (r * tb.dxv[l] * inv_veh_len);
                 }
-                if (a.qk) rew -= q * q * a.dt;
             }
             __syncthreads();
             p ^= 1;
+            if (rt) rt += 2 * L;
+            if (sig_t) sig_t += L;
+            if (inc_t) inc_t += L;
         }
         if (reward) {   // fixed-order tree reduction of the per-thread partial sums
             red[threadIdx.x] = rew;
@@ -145,14 +151,17 @@ __global__ void __launch_bounds__(256) net_rollout_fwd_kernel(NetArgs<T> a, cons
 // g_reward [R]            optional: dLoss/d reward (fused queue reward)
 // outputs: g_r0, g_y0, g_u0 [R][NC]; g_own0 [R][n_own][2]; g_sig, g_inc [R][T][L]
 template <typename T>
-__global__ void __launch_bounds__(256, 2) net_rollout_bwd_kernel(NetArgs<T> a, const T* __restrict__ hist, const T* __restrict__ ownh,
+__global__ void __launch_bounds__(512) net_rollout_bwd_kernel(NetArgs<T> a, const T* __restrict__ hist, const T* __restrict__ ownh,
                                                                const T* __restrict__ g_states, const T* __restrict__ g_reward,
                                                                T* __restrict__ g_r0, T* __restrict__ g_y0, T* __restrict__ g_u0,
                                                                T* __restrict__ g_own0, T* __restrict__ g_sig,
                                                                T* __restrict__ g_inc, int* __restrict__ flags) {
     extern __shared__ __align__(16) unsigned char raw[];
-    T* sm = reinterpret_cast<T*>(raw);
-    const int NC = a.NC, L = a.L;
+    const int NC = a.NC, L = a.L, NI = NC + L;
+    unsigned char* pp = raw;
+    const NetTabs<T> tb = net_tabs_carve<T>(pp, a, NI);
+    const SideTab<T> sd = side_tab_carve<T>(pp, L);
+    T* sm = reinterpret_cast<T*>(pp);
     // three rotating state buffers: state t (cur), state t + 1 (nxt) and the row being prefetched for the next step
     // (pre); the stored rows stream in with cp.async (LDGSTS) one step ahead of the arithmetic
     T* cur = sm;                        // state t      (r, y, u)
@@ -162,10 +171,11 @@ __global__ void __launch_bounds__(256, 2) net_rollout_bwd_kernel(NetArgs<T> a, c
     T* own = sm + 12 * NC;              // own records at step t
     T* own_pre = own + 2 * a.n_own;     // own records at step t - 1, in flight
     T* GO = own_pre + 2 * a.n_own;      // adjoint of the own records
-    T* pub = GO + 2 * a.n_own;          // [L][2 sides][3] published (d green r, d green u, d signal)
-    int* order = reinterpret_cast<int*>(pub + (size_t)6 * L);      // [L] lanes by decreasing number of cells
-    const T inv_umax = T(1) / a.umax, inv15 = T(1) / (T(1.5) * a.umax);
-    lane_order(a, order);
+    T* gh = GO + 2 * a.n_own;           // [2][L][2] final ghost (r, u) of step t
+    T* ab = gh + 4 * L;                 // [NI][4] A^T w, B^T w per interface
+    T* pub = ab + 4 * (size_t)NI;       // [L][2 sides][3] published (d green r, d green u, d signal)
+    T* gq = pub + (size_t)6 * L;        // [NC] queue-reward sigmoid of every cell of state t + 1
+    net_tabs_init(a, tb);
     for (int b = blockIdx.x; b < a.R; b += gridDim.x) {
         __syncthreads();
         {   // terminal state and adjoint
@@ -177,6 +187,11 @@ __global__ void __launch_bounds__(256, 2) net_rollout_bwd_kernel(NetArgs<T> a, c
             for (int c = threadIdx.x; c < 2 * a.n_own; c += blockDim.x) GO[c] = T(0);
         }
         const T grew = g_reward ? g_reward[b] : T(0);
+        const bool fused = a.qk && g_reward;
+        const T inv_veh_len = T(1) / a.veh_len;
+        const int* rt0 = a.route ? a.route + (size_t)b * a.route_stride : nullptr;
+        const T* sig0 = a.sig ? a.sig + (size_t)b * a.T_steps * L : nullptr;
+        const T* inc0 = a.incoming ? a.incoming + (size_t)b * a.T_steps * L : nullptr;
         bool nan = false;
 #define DHTS_NET_PREFETCH(TT, DST, ODST)                                                                               \
         {                                                                                                              \
@@ -192,94 +207,75 @@ __global__ void __launch_bounds__(256, 2) net_rollout_bwd_kernel(NetArgs<T> a, c
             __syncthreads();          // state t has landed; the previous step's gathers are complete
             if (t > 0) DHTS_NET_PREFETCH(t - 1, pre, own_pre)          // pre was state t + 2: nobody reads it any more
             const T* cr = cur; const T* cy = cur + NC; const T* cu = cur + 2 * NC;
-            const int* rt = a.route ? a.route + (size_t)b * a.route_stride + (size_t)t * 2 * L : nullptr;
-            const T* sig_t = a.sig ? a.sig + ((size_t)b * a.T_steps + t) * L : nullptr;
-            const T* inc_t = a.incoming ? a.incoming + ((size_t)b * a.T_steps + t) * L : nullptr;
+            const int* rt = rt0 ? rt0 + (size_t)t * 2 * L : nullptr;
+            const T* sig_t = sig0 ? sig0 + (size_t)t * L : nullptr;
+            const T* inc_t = inc0 ? inc0 + (size_t)t * L : nullptr;
             bool dummy = false;
-            for (int li = threadIdx.x; li < L; li += blockDim.x) {
-                const int l = order[li];
-                const int c0 = a.cell_off[l], N = a.cell_off[l + 1] - c0;
-                const T dxl = a.dx[l], cc = a.dt / dxl;
-                // (1) fused queue reward of state t+1 and the stored speed's adjoint folded into (r, y)
-                if (a.qk && g_reward) {
-                    T q = T(0);
-                    for (int i = 0; i < N; i++) {
-                        T z = (a.static_speed - nxt[2 * NC + c0 + i]) * a.qk[t];
-                        z = z < T(-16) ? T(-16) : (z > T(16) ? T(16) : z);
-                        q += sigm(z) * (nxt[c0 + i] * dxl / a.veh_len);
-                    }
-                    const T gq = -T(2) * q * a.dt * grew;
-                    for (int i = 0; i < N; i++) {
-                        const T zr = (a.static_speed - nxt[2 * NC + c0 + i]) * a.qk[t];
-                        const bool in = zr >= T(-16) && zr <= T(16);
-                        const T z = zr < T(-16) ? T(-16) : (zr > T(16) ? T(16) : zr);
-                        const T sg = sigm(z), w = dxl / a.veh_len;
-                        G[c0 + i] += gq * sg * w;
-                        if (in) G[2 * NC + c0 + i] += gq * nxt[c0 + i] * w * sg * (T(1) - sg) * (-a.qk[t]);
-                    }
+            // ---- A0: the queue-reward sigmoid of every cell of state t + 1 (fused queue reward), once
+            if (fused) {
+                const T qk = a.qk[t];
+                for (int c = threadIdx.x; c < NC; c += blockDim.x) {
+                    const T zr = (a.static_speed - nxt[2 * NC + c]) * qk;
+                    const T z = zr < T(-16) ? T(-16) : (zr > T(16) ? T(16) : zr);
+                    gq[c] = sigm(z);
                 }
-                for (int i = 0; i < N; i++) {
-                    T dr, dy; du_dry(nxt[c0 + i], nxt[NC + c0 + i], a.umax, dr, dy);
-                    const T gu = G[2 * NC + c0 + i];
-                    G[c0 + i] += gu * dr; G[NC + c0 + i] += gu * dy;
+                __syncthreads();
+            }
+            // ---- A: per cell, reward adjoint and the stored speed's adjoint folded into (r, y); per (side, lane), ghosts of step t
+            for (int c = threadIdx.x; c < NC; c += blockDim.x) {
+                T gr = G[c], gy = G[NC + c], gu = G[2 * NC + c];
+                if (fused) {
+                    const int l = tb.lane_of_cell[c];
+                    const T w = tb.dxv[l] * inv_veh_len;
+                    T q = T(0);                                            // queue length of the cell's lane (<= a few cells)
+                    for (int j = a.cell_off[l]; j < a.cell_off[l + 1]; j++) q += gq[j] * (nxt[j] * w);
+                    const T glq = -T(2) * q * a.dt * grew;                 // d loss / d (queue length of the lane)
+                    const T qk = a.qk[t];
+                    const T zr = (a.static_speed - nxt[2 * NC + c]) * qk;
+                    const bool in = zr >= T(-16) && zr <= T(16);
+                    const T sg = gq[c];
+                    gr += glq * sg * w;
+                    if (in) gu += glq * nxt[c] * w * sg * (T(1) - sg) * (-qk);
                 }
-                // (2) ghosts of step t and the flux-difference adjoint over the lane's interfaces
-                const Side<T> sl = resolve_side(a, l, 0, rt, cr, cu, own, sig_t, inc_t, dummy);
-                const Side<T> sr = resolve_side(a, l, 1, rt, cr, cu, own, sig_t, inc_t, dummy);
-                const Cell<T> gL = ghost_cell<T, true>(sl.fr, sl.fu, a.umax);
-                const Cell<T> gR = ghost_cell<T, true>(sr.fr, sr.fu, a.umax);
-                Cell<T> Lc = gL;
-                T gLr = T(0), gLy = T(0);            // old adjoint of the cell left of the interface (ghost: 0)
-                T pbr = T(0), pby = T(0);            // B^T w of the previous interface
-                T ggl_r = T(0), ggl_y = T(0), ggr_r = T(0), ggr_y = T(0);
-                for (int i = 0; i <= N; i++) {
-                    const Cell<T> Rc = (i < N) ? derive_cell_stored<T, true>(cr[c0 + i], cy[c0 + i], cu[c0 + i], T(0), false, a.umax) : gR;
-                    const T gRr = (i < N) ? G[c0 + i] : T(0), gRy = (i < N) ? G[NC + c0 + i] : T(0);
-                    const Riem<T> o = riemann(Lc, Rc, a.umax, inv_umax, inv15, a.dt, dxl);
-                    T par, pay, qbr, qby;
-                    riemann_adj(Lc, Rc, o, a.umax, inv_umax, inv15, gRr - gLr, gRy - gLy, par, pay, qbr, qby);
-                    if (i == 0) { ggl_r = cc * par; ggl_y = cc * pay; }
-                    else {
-                        const T nr_ = gLr + cc * (par + pbr), ny_ = gLy + cc * (pay + pby);
-                        nan |= t_isnan(nr_) || t_isnan(ny_);
-                        G[c0 + i - 1] = nr_; G[NC + c0 + i - 1] = ny_;
-                    }
-                    if (i == N) { ggr_r = cc * qbr; ggr_y = cc * qby; }
-                    pbr = qbr; pby = qby; gLr = gRr; gLy = gRy; Lc = Rc;
-                }
-                for (int i = 0; i < N; i++) G[2 * NC + c0 + i] = T(0);      // the stored speed of state t: filled by the gathers
-                // (3) ghost adjoint -> from_r_u -> blend -> (d green, d signal) per side
-                for (int side = 0; side < 2; side++) {
-                    const Side<T>& s = side == 0 ? sl : sr;
-                    const T g_r = side == 0 ? ggl_r : ggr_r, g_y = side == 0 ? ggl_y : ggr_y;
-                    const T ue = u_eq(s.fr, a.umax);
-                    T gfr = g_r + g_y * (s.fu - ue - s.fr * u_eq_true_prime(s.fr, a.umax));
-                    T gfu = g_y * s.fr;
-                    const int os = a.own_slot[side * L + l];
-                    if (os >= 0) { gfr += GO[2 * os]; gfu += GO[2 * os + 1]; }       // own_{t+1} = final_t
-                    T ggr = gfr, ggu = gfu, gs = T(0);
-                    if (a.mode == 1) {
-                        const T red_r = side == 0 ? T(0) : T(1), red_u = side == 0 ? a.umax : T(0);
-                        ggr = gfr * s.s; ggu = gfu * s.s;
-                        gs = gfr * (s.gr_ - red_r) + gfu * (s.gu_ - red_u);
-                        if (side == 1) gs = a.soft ? gs * T(32) * s.s * (T(1) - s.s) : T(0);
-                        if (s.sig_lane < 0) gs = T(0);
-                    }
-                    if (os >= 0) {
-                        const bool own_src = s.src == -1;
-                        GO[2 * os] = own_src ? ggr : T(0); GO[2 * os + 1] = own_src ? ggu : T(0);
-                    }
-                    if (s.src == -2 && g_inc)
-                        g_inc[((size_t)b * a.T_steps + t) * L + l] = ggr + ggu * u_eq_true_prime(s.gr_, a.umax);
-                    T* pb = pub + ((size_t)l * 2 + side) * 3;
-                    pb[0] = s.src >= 0 ? ggr : T(0); pb[1] = s.src >= 0 ? ggu : T(0); pb[2] = gs;
-                }
-                if (g_inc && !(a.mode == 1 && a.nadj[l] == 0)) g_inc[((size_t)b * a.T_steps + t) * L + l] = T(0);
+                T dr, dy; du_dry(nxt[c], nxt[NC + c], a.umax, dr, dy);
+                G[c] = gr + gu * dr; G[NC + c] = gy + gu * dy;
+            }
+            for (int q = threadIdx.x; q < 2 * L; q += blockDim.x) {
+                const int side = q >= L, l = q - side * L;
+                const Side<T> s = resolve_side(a, l, side, rt, cr, cu, own, sig_t, inc_t, dummy);
+                gh[2 * q] = s.fr; gh[2 * q + 1] = s.fu;
+                sd.src[q] = s.src; sd.sig_lane[q] = s.sig_lane; sd.s[q] = s.s; sd.gr[q] = s.gr_; sd.gu[q] = s.gu_;
             }
             __syncthreads();
-            // (4) gathers: what the neighbours took from this lane's edge cells and from its signal
-            for (int li = threadIdx.x; li < L; li += blockDim.x) {
-                const int l = order[li];
+            // ---- I: flux-difference adjoint, one thread per interface
+            net_adj_flux<T>(a, tb, cr, cy, cu, nullptr, gh, G, G + NC, ab);
+            __syncthreads();
+            // ---- C: per cell, the adjoint of state t (before the gathers) with the injected adjoint; per (side, lane), the
+            // ghost adjoint pulled through from_r_u and the blend
+            for (int c = threadIdx.x; c < NC; c += blockDim.x) {
+                const int l = tb.lane_of_cell[c];
+                const int it = tb.if_off[l] + (c - a.cell_off[l]);      // interface on the cell's left; it + 1 on its right
+                const T cc = tb.cc[l];
+                T nr_ = fma(cc, ab[4 * (it + 1)] + ab[4 * it + 2], G[c]);
+                T ny_ = fma(cc, ab[4 * (it + 1) + 1] + ab[4 * it + 3], G[NC + c]);
+                nan |= t_isnan(nr_) || t_isnan(ny_);
+                T nu_ = T(0);                                             // the stored speed of state t: filled by the gathers
+                if (g_states && t > 0) {
+                    const T* gs_ = g_states + ((size_t)(t - 1) * a.R + b) * 3 * NC;
+                    nr_ += gs_[c]; ny_ += gs_[NC + c]; nu_ = gs_[2 * NC + c];
+                }
+                G[c] = nr_; G[NC + c] = ny_; G[2 * NC + c] = nu_;
+            }
+            for (int q = threadIdx.x; q < 2 * L; q += blockDim.x) {
+                const int side = q >= L, l = q - side * L;
+                const T cc = tb.cc[l];
+                const T* o = ab + 4 * (size_t)(side == 0 ? tb.if_off[l] : tb.if_off[l + 1] - 1);
+                const T g_r = cc * (side == 0 ? o[0] : o[2]), g_y = cc * (side == 0 ? o[1] : o[3]);
+                net_adj_side<T>(a, gh, l, side, sd.src[q], sd.sig_lane[q], sd.s[q], sd.gr[q], sd.gu[q], g_r, g_y, GO, pub, g_inc ? g_inc + ((size_t)b * a.T_steps + t) * L : nullptr);
+            }
+            __syncthreads();
+            // ---- gathers, one thread per lane: what the neighbours took from this lane's edge cells and from its signal
+            for (int l = threadIdx.x; l < L; l += blockDim.x) {
                 const int c0 = a.cell_off[l], N = a.cell_off[l + 1] - c0;
                 T gsig = pub[((size_t)l * 2 + 1) * 3 + 2];
                 // successors whose LEFT ghost came from this lane's last cell / was blended by this lane's signal
@@ -303,13 +299,6 @@ __global__ void __launch_bounds__(256, 2) net_rollout_bwd_kernel(NetArgs<T> a, c
                 }
                 if (g_sig) g_sig[((size_t)b * a.T_steps + t) * L + l] = gsig;
                 nan |= t_isnan(gsig);
-                // (5) injected adjoint of state t (it is the state after step t - 1)
-                if (g_states && t > 0) {
-                    const T* gs_ = g_states + ((size_t)(t - 1) * a.R + b) * 3 * NC;
-                    for (int i = 0; i < N; i++) {
-                        G[c0 + i] += gs_[c0 + i]; G[NC + c0 + i] += gs_[NC + c0 + i]; G[2 * NC + c0 + i] += gs_[2 * NC + c0 + i];
-                    }
-                }
             }
             { T* x_ = nxt; nxt = cur; cur = pre; pre = x_; x_ = own; own = own_pre; own_pre = x_; }     // rotate: no copy, no barrier
         }
@@ -335,11 +324,16 @@ static int net_sm_count() {
     }
     return n;
 }
-static int net_threads(int L) { int t = (L + 31) / 32 * 32; return t > 256 ? 256 : (t < 32 ? 32 : t); }
-
-template <typename T> static size_t net_smem(int L, int NC, int n_own, bool adj, int threads) {
-    return sizeof(T) * (adj ? ((size_t)12 * NC + 6 * n_own + (size_t)6 * L) : ((size_t)6 * NC + 4 * n_own + threads)) + sizeof(int) * (size_t)L + 16;
+// Few replicas (latency-bound: a CTA's step time is what counts): one thread per interface, NC + L of them, up to 512.
+// Many replicas (throughput-bound: several CTAs per SM hide each other's barriers): half as many threads, each looping
+// twice, so that two CTAs of the 128-register adjoint fit an SM.
+static int net_threads(int L, int NC, int R) {
+    int ni = NC + L;
+    if (R > net_sm_count()) ni = (ni + 1) / 2;
+    int t = (ni + 31) / 32 * 32;
+    return t > 512 ? 512 : (t < 32 ? 32 : t);
 }
+
 
 template <typename T>
 static int net_check(const NetArgs<T>& a) {
@@ -372,7 +366,7 @@ static int net_fwd(const NetArgs<T>& a, const T* r0, const T* y0, const T* u0, c
     if (rc) return rc;
     if (!r0 || !y0 || !u0 || !hist || !flags || (a.n_own > 0 && (!own0 || !ownh))) return DHTS_ERR_INVALID;
     if (a.R == 0) return DHTS_OK;
-    const int threads = net_threads(a.L);
+    const int threads = net_threads(a.L, a.NC, a.R);
     const size_t smem = net_smem<T>(a.L, a.NC, a.n_own, false, threads);
     int grid = 1;
     rc = net_launch_cfg<T>(net_rollout_fwd_kernel<T>, smem, threads, a.R, &grid);
@@ -388,7 +382,7 @@ static int net_bwd(const NetArgs<T>& a, const T* hist, const T* ownh, const T* g
     if (rc) return rc;
     if (!hist || !g_r0 || !g_y0 || !g_u0 || !flags || (a.n_own > 0 && !ownh)) return DHTS_ERR_INVALID;
     if (a.R == 0) return DHTS_OK;
-    const int threads = net_threads(a.L);
+    const int threads = net_threads(a.L, a.NC, a.R);
     const size_t smem = net_smem<T>(a.L, a.NC, a.n_own, true, threads);
     int grid = 1;
     rc = net_launch_cfg<T>(net_rollout_bwd_kernel<T>, smem, threads, a.R, &grid);
