@@ -393,7 +393,7 @@ class Batch:
             self.chunk, self.K = F.arz_rollout_plan(B, N, T, dt_t, dev)
         self.chunks = [(lo, min(B, lo + self.chunk)) for lo in range(0, B, self.chunk)]
         # one checkpoint arena for all chunks and passes (a chunk's checkpoints are dead once its adjoint has run)
-        self.arena = torch.empty(((T + self.K - 1) // self.K) * 2 * self.chunk * N, dtype=dt_t, device=dev)
+        self.arena = torch.empty(F.arz_ckpt_elems(self.chunk, N, T, self.K, dt_t), dtype=dt_t, device=dev)   # states (+ interface outcomes)
 
     def ev(self):
         return self.torch.cuda.Event(enable_timing=True)

@@ -183,24 +183,27 @@ template <typename T> struct Shm {
     T* boxL;          // [2][nwarp][RF_ADJ]
     T* boxR;          // [2][nwarp][4]
 };
-template <typename T> __host__ __device__ inline size_t shm_bytes(int lpc, int nwarp) {
-    return sizeof(LaneK<T>) * lpc + sizeof(T) * ((size_t)lpc * 4 * (GH_F + GH_A) + (size_t)2 * nwarp * (RF_ADJ + 4)) + 16;
+// fwd: the forward kernel's layout -- no adjoint ghost records, forward-sized mailbox (keeps the 3-stage, 3-row staging
+// ring of a 1024-cell lane under the 74 KB of three CTAs per SM)
+template <typename T> __host__ __device__ inline size_t shm_bytes(int lpc, int nwarp, bool fwd = false) {
+    return sizeof(LaneK<T>) * lpc +
+           sizeof(T) * ((size_t)lpc * 4 * (GH_F + (fwd ? 0 : GH_A)) + (size_t)2 * nwarp * ((fwd ? RF_FWD : RF_ADJ) + 4)) + 16;
 }
-template <typename T> __host__ __device__ inline size_t ring_offset(int lpc, int nwarp) {
-    return (shm_bytes<T>(lpc, nwarp) + 127) / 128 * 128;
+template <typename T> __host__ __device__ inline size_t ring_offset(int lpc, int nwarp, bool fwd = false) {
+    return (shm_bytes<T>(lpc, nwarp, fwd) + 127) / 128 * 128;
 }
-template <typename T> __device__ __forceinline__ Shm<T> carve_shm(unsigned char* raw, int lpc, int nwarp) {
+template <typename T> __device__ __forceinline__ Shm<T> carve_shm(unsigned char* raw, int lpc, int nwarp, bool fwd = false) {
     Shm<T> s;
     s.lk = reinterpret_cast<LaneK<T>*>(raw);
     T* p = reinterpret_cast<T*>(raw + sizeof(LaneK<T>) * lpc);
-    s.ghostF = p; p += lpc * 4 * GH_F; s.ghostA = p; p += lpc * 4 * GH_A;
-    s.boxL = p; p += 2 * nwarp * RF_ADJ; s.boxR = p;
+    s.ghostF = p; p += lpc * 4 * GH_F; s.ghostA = p; p += fwd ? 0 : lpc * 4 * GH_A;
+    s.boxL = p; p += 2 * nwarp * (fwd ? RF_FWD : RF_ADJ); s.boxR = p;
     return s;
 }
 
 template <typename T>
 __device__ __forceinline__ void setup_group(const Shm<T>& s, int lane0, int nl, const T* __restrict__ ghost,
-                                            const T* __restrict__ dx, const T* __restrict__ umax_, T dt) {
+                                            const T* __restrict__ dx, const T* __restrict__ umax_, T dt, bool fwd = false) {
     for (int l = threadIdx.x; l < nl; l += blockDim.x) s.lk[l] = make_lanek<T>(umax_[lane0 + l], dx[lane0 + l], dt);
     for (int e = threadIdx.x; e < nl * 2 && ghost; e += blockDim.x) {      // ghost == null: per-step ghosts (step_ghost_record)
         int l = e >> 1, side = e & 1;
@@ -209,6 +212,7 @@ __device__ __forceinline__ void setup_group(const Shm<T>& s, int lane0, int nl, 
         FRec<T> f = fderive<T, true>(g[0], g[1], g[2], k);
         if (g[0] < DHTS_EPS) f.w = w_vacuum(g[0], f.us, k);
         pack(f, s.ghostF + (l * 2 + side) * GH_F);
+        if (fwd) continue;
         ARec<T> a = aderive<T, true>(g[0], g[1], g[2], k);
         if (g[0] < DHTS_EPS) fix_vacuum_adj(a, g[1], k);
         T tmp[RF_ADJ];
@@ -251,15 +255,18 @@ __device__ __forceinline__ FRec<T> fcell(T r, T y, T us, const LaneK<T>& k) {
     return c;
 }
 
-template <typename T, int C, bool STORED, bool CHECK, bool VAC>
+// XR: also collect the outcome of every interface (dhts_arz_lean.cuh): two bits per interface, the one on the left of cell c
+// at bits 2c, 2c + 1 of `ob` -- one halfword per thread and step, which the adjoint (same thread -> cell mapping) reads back.
+template <typename T, int C, bool STORED, bool CHECK, bool VAC, bool XR>
 __device__ __forceinline__ bool chunk_fwd_sweep(T* r, T* y, const T* us, const FRec<T>& last, FRec<T>& L,
-                                                const LaneK<T>& k, T dt, T* f0, T& fpr, T& fpy, bool& okL) {
+                                                const LaneK<T>& k, T dt, T* f0, T& fpr, T& fpy, bool& okL, unsigned& ob) {
     bool bad = false;
 #pragma unroll
     for (int c = 0; c < C; c++) {
         const FRec<T> cur = (c == C - 1) ? last : fcell<T, STORED, VAC>(r[c], y[c], STORED ? us[c] : T(0), k);
         T fr, fy;
-        fflux<T, VAC>(L, cur.r, cur.us, k, fr, fy);
+        if (XR) { unsigned b2; fflux_x<T, VAC>(L, cur.r, cur.us, k, fr, fy, b2); ob |= b2 << (2 * c); }
+        else fflux<T, VAC>(L, cur.r, cur.us, k, fr, fy);
         if (CHECK) {
             const bool okR = cell_speed_ok(cur.us, cur.w, k);
             // never in a valid run; the vote makes the branch warp-uniform (no reconvergence bookkeeping around it): every
@@ -277,10 +284,11 @@ __device__ __forceinline__ bool chunk_fwd_sweep(T* r, T* y, const T* us, const F
     return bad;
 }
 
-template <typename T, int C, bool STORED, bool CHECK>
+// sx (XR): where this thread's outcome halfword of the step goes in the staging ring (null: inactive thread / not stored).
+template <typename T, int C, bool STORED, bool CHECK, bool XR = false>
 __device__ __forceinline__ bool chunk_fwd_step(T* r, T* y, const T* us, bool first_chunk, bool last_chunk,
                                                const LaneK<T>& k, const T* ghostL, const T* ghostR, T dt, T* boxL,
-                                               T* boxR, int warp, int nwarp, unsigned lane) {
+                                               T* boxR, int warp, int nwarp, unsigned lane, unsigned short* sx = nullptr) {
     const FRec<T> last = fcell<T, STORED, true>(r[C - 1], y[C - 1], STORED ? us[C - 1] : T(0), k);
     T mine[RF_FWD], left[RF_FWD];
     pack(last, mine);
@@ -293,8 +301,15 @@ __device__ __forceinline__ bool chunk_fwd_step(T* r, T* y, const T* us, bool fir
     T f0[2], fpr = T(0), fpy = T(0);
     bool bad;
     anyvac = __any_sync(FULL, anyvac);            // one variant per warp (a mixed warp would run both, one after the other)
-    if (__builtin_expect(anyvac, 0)) bad = chunk_fwd_sweep<T, C, STORED, CHECK, true>(r, y, us, last, L, k, dt, f0, fpr, fpy, okL);
-    else bad = chunk_fwd_sweep<T, C, STORED, CHECK, false>(r, y, us, last, L, k, dt, f0, fpr, fpy, okL);
+    unsigned ob = 0;
+    if (__builtin_expect(anyvac, 0)) bad = chunk_fwd_sweep<T, C, STORED, CHECK, true, XR>(r, y, us, last, L, k, dt, f0, fpr, fpy, okL, ob);
+    else bad = chunk_fwd_sweep<T, C, STORED, CHECK, false, XR>(r, y, us, last, L, k, dt, f0, fpr, fpy, okL, ob);
+    // (XR) the outcomes go into the step's stage; this fence -- before the step's second block barrier, after which the bulk
+    // store is issued -- also covers the (r, y) rows written at the top of the step
+    if (XR) {
+        if (sx) *sx = (unsigned short)ob;
+        fence_proxy_async();
+    }
     T fR[2];
     from_right<T, 2>(f0, fR, boxR, warp, nwarp, lane);
     if (last_chunk) {   // interface with the right ghost cell
@@ -312,7 +327,13 @@ __device__ __forceinline__ bool chunk_fwd_step(T* r, T* y, const T* us, bool fir
 // NS > 0 (every state stored, K == 1): the state rows go to HBM through an NS-stage shared-memory staging ring and
 // TMA bulk stores issued by one thread -- no per-thread STG, no store address arithmetic, and the state registers
 // are free again as soon as the STS has read them.  NS == 0: per-thread vector stores (sparse checkpoints).
-template <typename T, int C, int MB, int NS, bool TV = false>
+// XR (staged mode only): besides (r, y) every state stores the OUTCOME of each interface of the step taken from it -- one
+// halfword per thread, behind the states in `ckpt` -- which lets the adjoint skip the case tree (aflux_x) for half a byte
+// per cell-step of HBM traffic.
+template <typename T> __host__ __device__ inline size_t xrow_elems(int lpc, int tpl) {      // outcome row of a stage, in elements
+    return (((size_t)lpc * tpl * 2 + 15) / 16 * 16) / sizeof(T);
+}
+template <typename T, int C, int MB, int NS, bool TV = false, bool XR = false>
 __global__ void __launch_bounds__(1024 / (C < 4 ? C : 4), MB) arz_rollout_fwd_reg_kernel(const T* __restrict__ r0, const T* __restrict__ y0,
                                            const T* __restrict__ u0, const T* __restrict__ ghost,
                                            const T* __restrict__ ghost_t,
@@ -322,11 +343,11 @@ __global__ void __launch_bounds__(1024 / (C < 4 ? C : 4), MB) arz_rollout_fwd_re
     extern __shared__ __align__(128) unsigned char raw[];
     const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5;
     const unsigned lane = threadIdx.x & 31;
-    Shm<T> s = carve_shm<T>(raw, lpc, nwarp);
-    const size_t stage_elems = (size_t)2 * lpc * N;
-    T* stg = reinterpret_cast<T*>(raw + ring_offset<T>(lpc, nwarp));     // [NS][2][lpc * N]
-    int stg_i = 0;
+    Shm<T> s = carve_shm<T>(raw, lpc, nwarp, true);
     const int tpl = N / C;                        // threads per lane
+    const size_t stage_elems = (size_t)2 * lpc * N + (XR ? xrow_elems<T>(lpc, tpl) : 0);
+    T* stg = reinterpret_cast<T*>(raw + ring_offset<T>(lpc, nwarp, true));     // [NS][(r, y) x lpc * N | outcomes]
+    int stg_i = 0;
     const int l = threadIdx.x / tpl, kc = threadIdx.x - l * tpl;
     const int ngroup = (B + lpc - 1) / lpc;
     bool bad = false;
@@ -335,7 +356,7 @@ __global__ void __launch_bounds__(1024 / (C < 4 ? C : 4), MB) arz_rollout_fwd_re
         const bool active = l < nl;
         const int ll = active ? l : 0;
         __syncthreads();
-        setup_group(s, lane0, nl, ghost, dx, umax_, dt);
+        setup_group(s, lane0, nl, ghost, dx, umax_, dt, true);
         __syncthreads();
         const LaneK<T> k = s.lk[ll];
         const T* gL = s.ghostF + (ll * 2) * GH_F; const T* gR = gL + GH_F;
@@ -350,7 +371,7 @@ __global__ void __launch_bounds__(1024 / (C < 4 ? C : 4), MB) arz_rollout_fwd_re
         T r[C], y[C];
         load_chunk<T, C>(r0 + off, r); load_chunk<T, C>(y0 + off, y);
         bool lbad = false;
-        T* blA = s.boxL; T* blB = s.boxL + nwarp * RF_ADJ;        // double-buffered mailboxes, swapped every step
+        T* blA = s.boxL; T* blB = s.boxL + nwarp * RF_FWD;        // double-buffered mailboxes, swapped every step
         T* brA = s.boxR; T* brB = s.boxR + nwarp * 4;
         T* ck = ckpt ? ckpt + off : nullptr;                       // next checkpoint slot of this chunk
         T* ckrow = ckpt ? ckpt + (size_t)lane0 * N : nullptr;      // same, start of the group's rows (bulk stores)
@@ -371,7 +392,7 @@ __global__ void __launch_bounds__(1024 / (C < 4 ? C : 4), MB) arz_rollout_fwd_re
                     // top of step t - 1, before that step's block barriers.
                     T* sp = stg + (size_t)stg_i * stage_elems + soff;
                     if (active) { store_chunk<T, C>(sp, r); store_chunk<T, C>(sp + (size_t)lpc * N, y); }
-                    fence_proxy_async();
+                    if (!XR) fence_proxy_async();
                     if (threadIdx.x == 0) bulk_wait_read<(NS > 2 ? NS - 2 : 0)>();
                 } else {
                     if (active) { store_chunk<T, C>(ck, r); store_chunk<T, C>(ck + BN, y); }
@@ -379,12 +400,15 @@ __global__ void __launch_bounds__(1024 / (C < 4 ? C : 4), MB) arz_rollout_fwd_re
                 }
                 next_ck += K;
             }
+            unsigned short* sx = (XR && store_now && active)
+                                     ? reinterpret_cast<unsigned short*>(stg + (size_t)stg_i * stage_elems + (size_t)2 * lpc * N) + ll * tpl + kc
+                                     : nullptr;
             if (t == 0 && u0) {
                 T us[C];
                 load_chunk<T, C>(u0 + off, us);
-                lbad |= chunk_fwd_step<T, C, true, true>(r, y, us, first_chunk, last_chunk, k, gL, gR, dt, blA, brA, warp, nwarp, lane);
+                lbad |= chunk_fwd_step<T, C, true, true, XR>(r, y, us, first_chunk, last_chunk, k, gL, gR, dt, blA, brA, warp, nwarp, lane, sx);
             } else
-                lbad |= chunk_fwd_step<T, C, false, true>(r, y, nullptr, first_chunk, last_chunk, k, gL, gR, dt, blA, brA, warp, nwarp, lane);
+                lbad |= chunk_fwd_step<T, C, false, true, XR>(r, y, nullptr, first_chunk, last_chunk, k, gL, gR, dt, blA, brA, warp, nwarp, lane, sx);
             T* x = blA; blA = blB; blB = x; x = brA; brA = brB; brB = x;
             if (NS > 0 && store_now) {
                 // every thread has passed the step's block barriers: the stage is complete and fenced
@@ -392,6 +416,9 @@ __global__ void __launch_bounds__(1024 / (C < 4 ? C : 4), MB) arz_rollout_fwd_re
                     const T* sp = stg + (size_t)stg_i * stage_elems;
                     bulk_s2g(ckrow, sp, rowbytes);
                     bulk_s2g(ckrow + BN, sp + (size_t)lpc * N, rowbytes);
+                    if (XR)      // outcome halfwords of the group's lanes: behind the `steps` stored states
+                        bulk_s2g(reinterpret_cast<unsigned short*>(ckpt + (size_t)steps * 2 * BN) + ((size_t)t * B + lane0) * tpl,
+                                 sp + (size_t)2 * lpc * N, (unsigned)((size_t)nl * tpl * 2));
                     bulk_commit();
                 }
                 ckrow += 2 * BN;
@@ -424,16 +451,19 @@ __device__ __forceinline__ ARec<T> acell(T r, T y, T us, const LaneK<T>& k) {
     return c;
 }
 
-template <typename T, int C, bool STORED, bool VAC>
+// XR: the forward pass stored the outcome of every interface (bits 2c, 2c + 1 of ob: interface on the left of cell c) -> aflux_x.
+template <typename T, int C, bool STORED, bool VAC, bool XR>
 __device__ __forceinline__ bool chunk_adj_sweep(const T* r, const T* y, const T* us, T* gr, T* gy, const ARec<T>& last,
-                                                ARec<T>& L, T& gLr, T& gLy, const LaneK<T>& k, T* a0, T& bpr, T& bpy) {
+                                                ARec<T>& L, T& gLr, T& gLy, const LaneK<T>& k, T* a0, T& bpr, T& bpy,
+                                                unsigned ob) {
     bool nan = false;
 #pragma unroll
     for (int c = 0; c < C; c++) {
         const ARec<T> cur = (c == C - 1) ? last : acell<T, STORED, VAC>(r[c], y[c], STORED ? us[c] : T(0), k);
         const T gcr = gr[c], gcy = gy[c];
         T ar, ay, br, by;
-        aflux<T, VAC>(L, cur, gcr - gLr, gcy - gLy, k, ar, ay, br, by);
+        if (XR) aflux_x<T>(L, cur, gcr - gLr, gcy - gLy, k, ob >> (2 * c), ar, ay, br, by);
+        else aflux<T, VAC>(L, cur, gcr - gLr, gcy - gLy, k, ar, ay, br, by);
         if (c == 0) { a0[0] = ar; a0[1] = ay; }
         else {
             gr[c - 1] = fma(k.cc, ar + bpr, gLr);
@@ -444,25 +474,27 @@ __device__ __forceinline__ bool chunk_adj_sweep(const T* r, const T* y, const T*
     return nan;
 }
 
-template <typename T, int C, bool STORED>
+template <typename T, int C, bool STORED, bool XR = false>
 __device__ __forceinline__ bool chunk_adj_step(const T* r, const T* y, const T* us, T* gr, T* gy, bool first_chunk,
                                                bool last_chunk, const LaneK<T>& k, const T* ghostL, const T* ghostR,
-                                               T* accL, T* accR, T* boxL, T* boxR, int warp, int nwarp, unsigned lane) {
+                                               T* accL, T* accR, T* boxL, T* boxR, int warp, int nwarp, unsigned lane,
+                                               unsigned ob = 0) {
     const T rl = r[C - 1];
     const ARec<T> last = acell<T, STORED, true>(rl, y[C - 1], STORED ? us[C - 1] : T(0), k);
-    T mine[RF_ADJ], left[RF_ADJ];
-    pack(last, gr[C - 1], gy[C - 1], mine);
-    from_left<T, RF_ADJ>(mine, left, boxL, warp, lane);
-    ARec<T> L = first_chunk ? unpack_a(ghostL) : unpack_a(left);
-    T gLr = first_chunk ? T(0) : left[10], gLy = first_chunk ? T(0) : left[11];   // OLD adjoint of the cell on the left
+    constexpr int NF = XR ? RF_ADJX : RF_ADJ;     // the stored-outcome path hands over a shorter record (no r, no w)
+    T mine[NF], left[NF];
+    if (XR) pack_x(last, gr[C - 1], gy[C - 1], mine); else pack(last, gr[C - 1], gy[C - 1], mine);
+    from_left<T, NF>(mine, left, boxL, warp, lane);
+    ARec<T> L = first_chunk ? unpack_a(ghostL) : (XR ? unpack_x(left) : unpack_a(left));
+    T gLr = first_chunk ? T(0) : left[NF - 2], gLy = first_chunk ? T(0) : left[NF - 1];   // OLD adjoint of the cell on the left
     T a0[2], bpr = T(0), bpy = T(0);
     bool anyvac = maybe_vac(L.r) || maybe_vac(rl);
 #pragma unroll
     for (int c = 0; c < C - 1; c++) anyvac |= maybe_vac(r[c]);
     bool nan;
     anyvac = __any_sync(FULL, anyvac);            // one variant per warp
-    if (__builtin_expect(anyvac, 0)) nan = chunk_adj_sweep<T, C, STORED, true>(r, y, us, gr, gy, last, L, gLr, gLy, k, a0, bpr, bpy);
-    else nan = chunk_adj_sweep<T, C, STORED, false>(r, y, us, gr, gy, last, L, gLr, gLy, k, a0, bpr, bpy);
+    if (__builtin_expect(anyvac, 0)) nan = chunk_adj_sweep<T, C, STORED, true, XR>(r, y, us, gr, gy, last, L, gLr, gLy, k, a0, bpr, bpy, ob);
+    else nan = chunk_adj_sweep<T, C, STORED, false, XR>(r, y, us, gr, gy, last, L, gLr, gLy, k, a0, bpr, bpy, ob);
     T aR[2];
     from_right<T, 2>(a0, aR, boxR, warp, nwarp, lane);
     if (last_chunk) {   // interface with the right ghost (its updated-state adjoint is zero)
@@ -482,7 +514,8 @@ __device__ __forceinline__ bool chunk_adj_step(const T* r, const T* y, const T* 
 // each gets its own register allocation.)
 // EXT (MODE 1 only): per-step ghosts ghost_t [steps][B][2][3] with their adjoints g_ghost_t [steps][B][2][2], and g_hist
 // [steps][2][B][N], the adjoint of a loss that reads the state BEFORE every step (added once that step's VJP has run).
-template <typename T, int C, int MB, int MODE, bool EXT = false>
+// XR (MODE 0 only): the forward pass stored the interface outcomes behind the states (see the forward kernel).
+template <typename T, int C, int MB, int MODE, bool EXT = false, bool XR = false>
 __global__ void __launch_bounds__(1024 / (C < 4 ? C : 4), MB) arz_rollout_bwd_reg_kernel(const T* __restrict__ ckpt, const T* __restrict__ u0,
                                            const T* __restrict__ ghost, const T* __restrict__ ghost_t,
                                            const T* __restrict__ g_hist, T* __restrict__ g_ghost_t,
@@ -499,7 +532,7 @@ __global__ void __launch_bounds__(1024 / (C < 4 ? C : 4), MB) arz_rollout_bwd_re
     Shm<T> s = carve_shm<T>(raw, lpc, nwarp);
     // state ring of the every-state-stored adjoint: ring_ns stages of (r row, y row) of the CTA's lanes, filled by
     // TMA bulk copies that complete on one mbarrier per stage
-    const size_t stage_elems = (size_t)2 * lpc * N;
+    const size_t stage_elems = (size_t)2 * lpc * N + (XR ? xrow_elems<T>(lpc, N / C) : 0);
     T* ring = reinterpret_cast<T*>(raw + ring_offset<T>(lpc, nwarp));
     uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)ring_ns * stage_elems);
     if (MODE == 0) {
@@ -553,7 +586,9 @@ __global__ void __launch_bounds__(1024 / (C < 4 ? C : 4), MB) arz_rollout_bwd_re
             // step after the one that consumed it: by then every thread has passed that step's two block barriers,
             // i.e. has finished reading the stage.
             const unsigned rowbytes = (unsigned)((size_t)nl * N * sizeof(T));
+            const unsigned xbytes = (unsigned)((size_t)nl * tpl * 2);
             const T* src0 = ckpt + (size_t)lane0 * N;
+            const unsigned short* xg0 = reinterpret_cast<const unsigned short*>(ckpt + (size_t)steps * 2 * BN) + (size_t)lane0 * tpl;
             int issued = 0;
 #define DHTS_RING_ISSUE                                                                                  \
             {                                                                                            \
@@ -561,9 +596,10 @@ __global__ void __launch_bounds__(1024 / (C < 4 ? C : 4), MB) arz_rollout_bwd_re
                 T* dst_ = ring + (size_t)fill_st * stage_elems;                                          \
                 const T* src_ = src0 + (size_t)(steps - 1 - issued) * 2 * BN;                            \
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                             \
-                mbar_expect_tx(bar_, 2 * rowbytes);                                                      \
+                mbar_expect_tx(bar_, 2 * rowbytes + (XR ? xbytes : 0u));                                 \
                 bulk_g2s(dst_, src_, rowbytes, bar_);                                                    \
                 bulk_g2s(dst_ + (size_t)lpc * N, src_ + BN, rowbytes, bar_);                             \
+                if (XR) bulk_g2s(dst_ + (size_t)2 * lpc * N, xg0 + (size_t)(steps - 1 - issued) * B * tpl, xbytes, bar_); \
                 issued++;                                                                                \
                 if (++fill_st == ring_ns) fill_st = 0;                                                   \
             }
@@ -576,11 +612,12 @@ __global__ void __launch_bounds__(1024 / (C < 4 ? C : 4), MB) arz_rollout_bwd_re
                 // last read precedes the step's second block barrier
                 const T* r = ring + (size_t)use_st * stage_elems + soff;
                 const T* y = r + (size_t)lpc * N;
+                const unsigned ob = XR ? reinterpret_cast<const unsigned short*>(ring + (size_t)use_st * stage_elems + (size_t)2 * lpc * N)[ll * tpl + kc] : 0u;
                 if (++use_st == ring_ns) { use_st = 0; use_par ^= 1u; }
                 if (t == 0 && u0)
-                    { T us_[C]; load_chunk<T, C>(u0 + off, us_); nan |= chunk_adj_step<T, C, true>(r, y, us_, gr, gy, first_chunk, last_chunk, k, gLa, gRa, accL, accR, blA, brA, warp, nwarp, lane); }
+                    { T us_[C]; load_chunk<T, C>(u0 + off, us_); nan |= chunk_adj_step<T, C, true, XR>(r, y, us_, gr, gy, first_chunk, last_chunk, k, gLa, gRa, accL, accR, blA, brA, warp, nwarp, lane, ob); }
                 else
-                    nan |= chunk_adj_step<T, C, false>(r, y, nullptr, gr, gy, first_chunk, last_chunk, k, gLa, gRa, accL, accR, blA, brA, warp, nwarp, lane);
+                    nan |= chunk_adj_step<T, C, false, XR>(r, y, nullptr, gr, gy, first_chunk, last_chunk, k, gLa, gRa, accL, accR, blA, brA, warp, nwarp, lane, ob);
                 DHTS_SWAP_BOXES
             }
 #undef DHTS_RING_ISSUE
@@ -704,10 +741,10 @@ static int sm_count_r() {
 // thread capped at 128 registers (2 CTAs of 256 threads per SM) -- forward 57 ms vs 69-89 ms for the other
 // shapes, adjoint 97 ms (every state stored) / 149 ms (K = 32) vs 106-226 ms.
 // Tuning knobs (environment), read ONCE per process: cells per thread, adjoint ring stages, forward staging.
-struct Knobs { int c_fwd, c_bwd, ring, stage, mb_fwd; };
+struct Knobs { int c_fwd, c_bwd, ring, stage, mb_fwd, xrow; };
 static const Knobs& knobs() {
     static const Knobs k = [] {
-        Knobs x{4, 4, 4, 1, 3};
+        Knobs x{4, 4, 4, 1, 3, 1};
         auto cells = [](const char* name, int dflt) {
             const char* e = getenv(name);
             if (!e) e = getenv("DHTS_ARZ_C");
@@ -718,13 +755,14 @@ static const Knobs& knobs() {
         x.c_fwd = cells("DHTS_ARZ_C_FWD", 4); x.c_bwd = cells("DHTS_ARZ_C_BWD", 4);
         if (const char* e = getenv("DHTS_ARZ_RING")) x.ring = atoi(e);      // 0 = register prefetch
         if (const char* e = getenv("DHTS_ARZ_STAGE")) x.stage = atoi(e);    // 0 = per-thread stores
+        if (const char* e = getenv("DHTS_ARZ_XROW")) x.xrow = atoi(e);      // 0 = never store the interface outcomes
         if (const char* e = getenv("DHTS_ARZ_MB_FWD")) x.mb_fwd = atoi(e);  // 3 (default) = 80-register forward kernel, 3 CTAs per SM: 384 vs 393 ms per pass (r2c A/B); 2 = 128 registers
         return x;
     }();
     return k;
 }
 
-template <typename T> static int plan_reg(int B, int N, bool adj, RegPlan* p) {
+template <typename T> static int plan_reg(int B, int N, bool adj, RegPlan* p, bool xr = false) {
     const int want = adj ? knobs().c_bwd : knobs().c_fwd;
     int C = 1;
     for (int c = 8; c > 1; c >>= 1)
@@ -743,7 +781,7 @@ template <typename T> static int plan_reg(int B, int N, bool adj, RegPlan* p) {
     // Budget per CTA keeps two CTAs of the 128-register shape on an SM (227 KB usable, 1 KB reserved per CTA).
     p->ring_ns = 0; p->mode = 1;
     if (adj) {
-        const size_t stage = (size_t)2 * lpc * N * sizeof(T);
+        const size_t stage = ((size_t)2 * lpc * N + (xr ? xrow_elems<T>(lpc, tpl) : 0)) * sizeof(T);
         const size_t base = ring_offset<T>(lpc, p->threads / 32);
         const size_t budget = (C > 1 ? 112 : 224) * (size_t)1024;
         int ns = knobs().ring;
@@ -769,12 +807,41 @@ template <typename T> static int plan_reg(int B, int N, bool adj, RegPlan* p) {
 
 static int status_r() { return cudaGetLastError() == cudaSuccess ? DHTS_OK : DHTS_ERR_CUDA; }
 
+// Do the rollouts of this shape store the interface outcomes with the states (ckpt_mode 1)?  Yes when every state is stored
+// and the staged forward kernel and the ring adjoint both apply with the same thread -> cell mapping.  Callers ask
+// (dhts_arz_rollout_ckpt_elems_*), size `ckpt` accordingly and pass the mode to both calls.
+constexpr int NSF = 4;          // staging stages of the forward kernel
+template <typename T> static int ckpt_mode_plan(int B, int N, int K) {
+    if (!knobs().xrow || K != 1 || B <= 0 || N < 1) return 0;
+    RegPlan pf, pb;
+    if (plan_reg<T>(B, N, false, &pf) || pf.C <= 1 || ((size_t)N * sizeof(T)) % 16 != 0 || (N / pf.C) % 8 != 0) return 0;
+    const size_t stage = ((size_t)2 * pf.lpc * N + xrow_elems<T>(pf.lpc, N / pf.C)) * sizeof(T);
+    if (ring_offset<T>(pf.lpc, pf.threads / 32, true) + NSF * stage > 112 * 1024) return 0;
+    if (plan_reg<T>(B, N, true, &pb, true) || pb.mode != 0 || pb.C != pf.C || pb.lpc != pf.lpc) return 0;
+    return 1;
+}
+template <typename T> static long long ckpt_elems(int B, int N, int steps, int K, int* mode) {
+    if (B < 0 || N < 1 || steps < 0 || K < 1) return -1;
+    const int m = ckpt_mode_plan<T>(B, N, K);
+    if (mode) *mode = m;
+    const long long S = (steps + K - 1) / K;
+    long long n = S * 2 * (long long)B * N;
+    if (m) {
+        RegPlan pf;
+        plan_reg<T>(B, N, false, &pf);
+        n += ((long long)steps * B * (N / pf.C) * 2 + (long long)sizeof(T) - 1) / (long long)sizeof(T);
+    }
+    return n;
+}
+
 template <typename T>
 static int rollout_fwd(const T* r0, const T* y0, const T* u0, const T* ghost, const T* ghost_t, const T* dx, const T* umax,
-                       T dt, int B, int N, int steps, int K, T* ckpt, T* rT, T* yT, T* uT, int* flags, cudaStream_t st) {
+                       T dt, int B, int N, int steps, int K, int xmode, T* ckpt, T* rT, T* yT, T* uT, int* flags, cudaStream_t st) {
     if (!r0 || !y0 || (!ghost && !ghost_t) || !dx || !umax || !rT || !yT || !uT || !flags || B < 0 || N < 1 || steps < 0)
         return DHTS_ERR_INVALID;
     if (ckpt && K < 1) return DHTS_ERR_INVALID;
+    if (xmode != 0 && xmode != 1) return DHTS_ERR_INVALID;
+    if (xmode == 1 && (!ckpt || ghost_t || ckpt_mode_plan<T>(B, N, K) != 1)) return DHTS_ERR_INVALID;
     if (B == 0) return DHTS_OK;
     RegPlan p;
     int rc = plan_reg<T>(B, N, false, &p);
@@ -784,11 +851,25 @@ static int rollout_fwd(const T* r0, const T* y0, const T* u0, const T* ghost, co
     if (K < 1) K = 1;
     int grid = p.grid;
     // every state stored: staging ring + TMA bulk stores when the rows are 16-byte sized and 4 stages fit
-    constexpr int NSF = 4;
     const size_t stage = (size_t)2 * p.lpc * N * sizeof(T);
-    const size_t base = ring_offset<T>(p.lpc, p.threads / 32);
+    const size_t base = ring_offset<T>(p.lpc, p.threads / 32, true);
     bool staged = ckpt && K == 1 && p.C > 1 && ((size_t)N * sizeof(T)) % 16 == 0 && base + NSF * stage <= 112 * 1024;
     if (knobs().stage == 0) staged = false;
+    if (xmode == 1) {   // staged, with the interface outcomes behind the states
+        if (!(al16(r0) && al16(y0) && al16(u0) && al16(ckpt))) return DHTS_ERR_UNSUPPORTED;
+        const size_t smem = base + NSF * (stage + xrow_elems<T>(p.lpc, N / p.C) * sizeof(T));
+#define CALL(CC, MB)                                                                                                   \
+    {                                                                                                                  \
+        cudaFuncSetAttribute(arz_rollout_fwd_reg_kernel<T, CC, MB, NSF, false, true>,                                  \
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                                  \
+        arz_rollout_fwd_reg_kernel<T, CC, MB, NSF, false, true><<<grid, p.threads, smem, st>>>(                        \
+            r0, y0, u0, ghost, nullptr, dx, umax, dt, B, N, steps, K, p.lpc, ckpt, rT, yT, uT, flags);                 \
+    }
+        // 128 registers (two CTAs per SM): at the 80 registers of three CTAs per SM the outcome bits spill (433 vs 410 ms per pass)
+        if (p.C == 8) { CALL(8, 2) } else if (p.C == 4) { CALL(4, 2) } else { CALL(2, 2) }
+#undef CALL
+        return status_r();
+    }
     if (ghost_t) {      // per-step ghosts: the variant with per-thread checkpoint stores
 #define CALL(CC, MB) arz_rollout_fwd_reg_kernel<T, CC, MB, 0, true><<<grid, p.threads, p.smem, st>>>(r0, y0, u0, nullptr, ghost_t, dx, umax, dt, B, N, steps, K, p.lpc, ckpt, rT, yT, uT, flags);
         DHTS_C_DISPATCH(p, CALL)
@@ -849,7 +930,7 @@ template <typename T> static long long rollout_scratch_elems(int B, int N, int K
 
 template <typename T>
 static int rollout_bwd(const T* ckpt, const T* u0, const T* ghost, const T* ghost_t, const T* dx, const T* umax, T dt, int B,
-                       int N, int steps, int K, const T* rT, const T* yT, const T* g_rT, const T* g_yT, const T* g_uT,
+                       int N, int steps, int K, int xmode, const T* rT, const T* yT, const T* g_rT, const T* g_yT, const T* g_uT,
                        const T* g_hist, T* scratch, long long scratch_elems, T* g_r0, T* g_y0, T* g_ghost, T* g_ghost_t,
                        int* flags, cudaStream_t st) {
     if (!ckpt || (!ghost && !ghost_t) || !dx || !umax || !g_r0 || !g_y0 || !flags || (!scratch && K > 1) || B < 0 || N < 1 || steps < 0 || K < 1)
@@ -857,7 +938,31 @@ static int rollout_bwd(const T* ckpt, const T* u0, const T* ghost, const T* ghos
     const bool ext = ghost_t || g_hist;
     if (ext && K != 1) return DHTS_ERR_INVALID;        // per-step ghosts / per-step adjoints need every state stored
     if (g_uT && (!rT || !yT)) return DHTS_ERR_INVALID;
+    if (xmode != 0 && xmode != 1) return DHTS_ERR_INVALID;
     if (B == 0) return DHTS_OK;
+    if (xmode == 1) {   // the interface outcomes were stored with the states: ring adjoint without the case tree
+        if (ext || ckpt_mode_plan<T>(B, N, K) != 1) return DHTS_ERR_INVALID;
+        RegPlan p;
+        int rc = plan_reg<T>(B, N, true, &p, true);
+        if (rc) return rc;
+        if (!(al16(ckpt) && al16(u0) && al16(g_r0) && al16(g_y0))) return DHTS_ERR_UNSUPPORTED;
+        int occ = 0, grid = 1;
+#define CALL(CC, MB)                                                                                                   \
+    {                                                                                                                  \
+        cudaFuncSetAttribute(arz_rollout_bwd_reg_kernel<T, CC, MB, 0, false, true>,                                       \
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);                                \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, arz_rollout_bwd_reg_kernel<T, CC, MB, 0, false, true>,        \
+                                                      p.threads, p.smem);                                              \
+        const long long g = (long long)sm_count_r() * (occ < 1 ? 1 : occ);                                             \
+        grid = (int)(g < p.grid ? g : p.grid);                                                                         \
+        arz_rollout_bwd_reg_kernel<T, CC, MB, 0, false, true><<<grid, p.threads, p.smem, st>>>(                           \
+            ckpt, u0, ghost, nullptr, nullptr, nullptr, dx, umax, dt, B, N, steps, K, p.lpc, rT, yT, g_rT, g_yT, g_uT, \
+            scratch, g_r0, g_y0, g_ghost, flags, p.ring_ns);                                                           \
+    }
+        if (p.C == 8) { CALL(8, 2) } else if (p.C == 4) { CALL(4, 2) } else { CALL(2, 2) }
+#undef CALL
+        return status_r();
+    }
     RegPlan p;
     int rc = plan_reg<T>(B, N, true, &p);
     if (rc) return rc;
@@ -894,22 +999,26 @@ static int rollout_bwd(const T* ckpt, const T* u0, const T* ghost, const T* ghos
 #define DHTS_ARZ_ROLLOUT_API(SUF, T)                                                                                   \
     DHTS_EXPORT int dhts_arz_rollout_fwd_##SUF(const T* r0, const T* y0, const T* u0, const T* ghost, const T* ghost_t, \
                                                const T* dx, const T* umax, T dt, int B, int N, int steps,              \
-                                               int ckpt_every, T* ckpt, T* rT, T* yT, T* uT, int* flags,               \
-                                               void* stream) {                                                         \
-        return dhts::rollout_fwd<T>(r0, y0, u0, ghost, ghost_t, dx, umax, dt, B, N, steps, ckpt_every, ckpt, rT, yT,   \
-                                    uT, flags, (cudaStream_t)stream);                                                  \
+                                               int ckpt_every, int ckpt_mode, T* ckpt, T* rT, T* yT, T* uT,            \
+                                               int* flags, void* stream) {                                             \
+        return dhts::rollout_fwd<T>(r0, y0, u0, ghost, ghost_t, dx, umax, dt, B, N, steps, ckpt_every, ckpt_mode,      \
+                                    ckpt, rT, yT, uT, flags, (cudaStream_t)stream);                                    \
+    }                                                                                                                  \
+    DHTS_EXPORT long long dhts_arz_rollout_ckpt_elems_##SUF(int B, int N, int steps, int ckpt_every, int* ckpt_mode) { \
+        return dhts::ckpt_elems<T>(B, N, steps, ckpt_every, ckpt_mode);                                                \
     }                                                                                                                  \
     DHTS_EXPORT long long dhts_arz_rollout_scratch_elems_##SUF(int B, int N, int ckpt_every) {                         \
         return dhts::rollout_scratch_elems<T>(B, N, ckpt_every);                                                       \
     }                                                                                                                  \
     DHTS_EXPORT int dhts_arz_rollout_bwd_##SUF(const T* ckpt, const T* u0, const T* ghost, const T* ghost_t,           \
                                                const T* dx, const T* umax, T dt, int B, int N, int steps,              \
-                                               int ckpt_every, const T* rT, const T* yT, const T* g_rT,                \
-                                               const T* g_yT, const T* g_uT, const T* g_hist, T* scratch,              \
+                                               int ckpt_every, int ckpt_mode, const T* rT, const T* yT,                \
+                                               const T* g_rT, const T* g_yT, const T* g_uT, const T* g_hist,           \
+                                               T* scratch,                                                             \
                                                long long scratch_elems, T* g_r0, T* g_y0, T* g_ghost, T* g_ghost_t,    \
                                                int* flags, void* stream) {                                             \
-        return dhts::rollout_bwd<T>(ckpt, u0, ghost, ghost_t, dx, umax, dt, B, N, steps, ckpt_every, rT, yT, g_rT,     \
-                                    g_yT, g_uT, g_hist, scratch, scratch_elems, g_r0, g_y0, g_ghost, g_ghost_t, flags, \
+        return dhts::rollout_bwd<T>(ckpt, u0, ghost, ghost_t, dx, umax, dt, B, N, steps, ckpt_every, ckpt_mode, rT,    \
+                                    yT, g_rT, g_yT, g_uT, g_hist, scratch, scratch_elems, g_r0, g_y0, g_ghost, g_ghost_t, flags, \
                                     (cudaStream_t)stream);                                                             \
     }
 

@@ -162,6 +162,23 @@ __device__ __forceinline__ void fflux(const FRec<T>& L, T Rr, T Rus, const LaneK
     fy = t.isL ? L.fy : y0 * u0;
 }
 
+// Stored interface outcome (forward -> adjoint through HBM): two bits per interface and step (bit 0: Q_L, bit 1: Q_M).  With
+// them the adjoint skips the case tree.  (Storing sqrt(r0 + eps) of the selected state as well -- 8 bytes per cell-step, so
+// that the adjoint skips that square root too -- was measured: adjoint 629 -> 580 ms per pass but forward 381 -> 411 ms, the
+// forward kernel does not take 24 instead of 16 bytes of writes per cell-step for free.)
+template <typename T, bool VAC = true>
+__device__ __forceinline__ void fflux_x(const FRec<T>& L, T Rr, T Rus, const LaneK<T>& k, T& fr, T& fy, unsigned& bits) {
+    const Tree<T> t = case_tree<T, VAC>(L.r, L.us, L.sq, L.w, Rr, Rus, k);
+    const T root = t.isM ? t.b : t.q;
+    const T r0 = root * root;
+    const T u0 = t.isM ? Rus : t.sc * (T(0.5) / T(1.5));
+    const T ueq = fma(-k.umax, f_sqrt_pos(r0 + DHTS_EPS), k.umax);
+    const T y0 = r0 * (u0 - ueq);
+    fr = t.isL ? L.fr : r0 * u0;
+    fy = t.isL ? L.fy : y0 * u0;
+    bits = (t.isL ? 1u : 0u) | (t.isM ? 2u : 0u);
+}
+
 // ---------------------------------------------------------------------------- adjoint
 constexpr int RF_ADJ = 12;
 // r, us, sq, w: case tree;  f00, f10, f11: flux_prime at the cell (Q_L outcome);  plr, ri: P_L;  gr, gy: adjoint
@@ -243,6 +260,57 @@ __device__ __forceinline__ void aflux(const ARec<T>& L, const ARec<T>& R, T wr, 
     const T cB = t.isM ? (r0z1 - cM) : T(0);
     pbr = cB * (R.plr + R.ueqp);
     pby = cB * R.ri;
+}
+
+// aflux with the interface's outcome stored by the forward pass (fflux_x): no case tree.
+// Uses us, sq, f00, f10, f11, plr, ri of L and us, plr, ri, ueqp of R.
+template <typename T>
+__device__ __forceinline__ void aflux_x(const ARec<T>& L, const ARec<T>& R, T wr, T wy, const LaneK<T>& k, unsigned bits, T& par,
+                                        T& pay, T& pbr, T& pby) {
+    const bool isL = bits & 1u, isM = bits & 2u;
+    const T b = fma(L.us - R.us, k.inv_umax, L.sq);                // Q_M: r_m = b^2
+    const T sc = fma(k.umax, L.sq, L.us);                          // Q_C: r_c = q^2, u_c = sc / 3
+    const T root = isM ? b : sc * k.inv15;
+    const T r0 = root * root;
+    const T rootr = t_abs(root);
+    const T u0 = isM ? R.us : sc * (T(0.5) / T(1.5));
+    const T ueq0 = fma(-k.umax, f_sqrt_pos(r0 + DHTS_EPS), k.umax);
+    const T g = u0 - ueq0;
+    const T y0 = r0 * g;
+    const bool big = r0 >= DHTS_EPS;
+    const T inv_sq = big ? f_rcp(rootr) : DHTS_RSQRT_EPS;
+    const T rr = big ? r0 : DHTS_EPS;
+    const T ueqp0 = -k.hum * inv_sq;
+    const T yr = y0 * (inv_sq * inv_sq);
+    const T f00 = fma(rr, ueqp0, ueq0);
+    const T f10 = fma(y0, ueqp0, -(yr * yr));
+    const T f11 = fma(T(2), yr, ueq0);
+    const T z0 = fma(f10, wy, f00 * wr);
+    const T z1 = fma(f11, wy, wr);
+    const T kk = fma(-r0, ueqp0, g);
+    const T s = fma(kk, z1, z0);
+    const T sa = s * (T(2) * rootr);
+    const T cM = sa * k.inv_umax;
+    const T r0z1 = r0 * z1;
+    const T cC = fma(sa, k.inv15, r0z1 * (T(0.5) / T(1.5)));
+    const T coef = isM ? cM : cC;
+    const T zl0 = fma(L.f10, wy, L.f00 * wr);
+    const T zl1 = fma(L.f11, wy, wr);
+    par = isL ? zl0 : coef * L.plr;
+    pay = isL ? zl1 : coef * L.ri;
+    const T cB = isM ? (r0z1 - cM) : T(0);
+    pbr = cB * (R.plr + R.ueqp);
+    pby = cB * R.ri;
+}
+// the mailbox record of that path: 8 fields of the cell + its old adjoint
+constexpr int RF_ADJX = 10;
+template <typename T> __device__ __forceinline__ void pack_x(const ARec<T>& c, T gr, T gy, T* a) {
+    a[0] = c.us; a[1] = c.sq; a[2] = c.f00; a[3] = c.f10; a[4] = c.f11; a[5] = c.plr; a[6] = c.ri; a[7] = c.ueqp; a[8] = gr; a[9] = gy;
+}
+template <typename T> __device__ __forceinline__ ARec<T> unpack_x(const T* a) {
+    ARec<T> c; c.r = T(0); c.w = T(0);
+    c.us = a[0]; c.sq = a[1]; c.f00 = a[2]; c.f10 = a[3]; c.f11 = a[4]; c.plr = a[5]; c.ri = a[6]; c.ueqp = a[7];
+    return c;
 }
 
 }  // namespace dhts

@@ -10,6 +10,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib
+from .ops import arz_ckpt_elems as _arz_ckpt_elems
 from .ops import (EPSILON, ArzRolloutFn, ArzStepFn, IdmRolloutFn, IdmStepFn, MacroToMicroFn, MicroToMacroFn,
                   csr_expand)
 
@@ -91,15 +92,22 @@ def idm_rollout_state(p0, v0, params, lane_off, head, dt, steps, ckpt_every, fla
     return IdmRolloutFn.apply(p0, v0, head, params, lane_off, max_lane, dt, steps, ckpt_every, flags.t, False)
 
 
+def arz_ckpt_elems(B, N, steps, ckpt_every, dtype) -> int:
+    """Elements a caller-owned ``ckpt_buffer`` must hold for a differentiable rollout of this shape: the stored states
+    [ceil(steps / ckpt_every), 2, B, N] plus, where the kernels store them, the interface outcomes of every step (half a byte
+    per cell-step; ``dhts_arz_rollout_ckpt_elems_*``, include/dhts.h)."""
+    return _arz_ckpt_elems(B, N, steps, ckpt_every, dtype)[0]
+
+
 def arz_rollout_plan(B, N, steps, dtype, device, mem_fraction=0.6, min_lanes=296):
     """How to run a differentiable rollout of B lanes within the device's free memory: returns
     (lanes_per_chunk, ckpt_every).  Storing EVERY state (ckpt_every = 1) removes the segment recompute from
-    the adjoint -- the fastest mode, 2 * N * steps scalars per lane -- so lanes are processed in chunks
+    the adjoint -- the fastest mode, 2 * N * steps scalars per lane (+ 1.6 % for the interface outcomes) -- so lanes are processed in chunks
     that fit `mem_fraction` of the free HBM (180 GB on B200: ~6500 lanes of 1024 cells x 1000 steps in
     fp64).  When not even `min_lanes` (two CTAs per SM) fit, fall back to sparse checkpoints + recompute."""
     esz = torch.empty((), dtype=dtype).element_size()
     free, _ = torch.cuda.mem_get_info(device)
-    per_lane = 2 * N * max(int(steps), 1) * esz
+    per_lane = -(-arz_ckpt_elems(min_lanes, N, max(int(steps), 1), 1, dtype) // min_lanes) * esz
     fit = int(free * mem_fraction) // per_lane
     if fit >= min(B, min_lanes):
         nchunk = -(-B // min(B, fit))                      # equal chunks (the last one may be a few lanes short)

@@ -104,6 +104,17 @@ def _lease_arena(buf):
     return lease
 
 
+def arz_ckpt_elems(B, N, steps, ckpt_every, dtype):
+    """(elements, ckpt_mode) of the checkpoint buffer of a differentiable rollout of this shape (include/dhts.h:
+    dhts_arz_rollout_ckpt_elems_*): the ceil(steps / ckpt_every) stored states [S, 2, B, N] and, in mode 1, the interface
+    outcomes of every step behind them."""
+    mode = ctypes.c_int(0)
+    n = int(_fn("arz_rollout_ckpt_elems", dtype)(int(B), int(N), int(steps), int(ckpt_every), ctypes.byref(mode)))
+    if n < 0:
+        raise ValueError("dhts_arz_rollout_ckpt_elems: invalid shape")
+    return n, int(mode.value)
+
+
 class ArzRolloutFn(torch.autograd.Function):
     """(r0, y0)[B,N], ghost -> (rT, yT, uT)[B,N] (+ hist) after `steps` fused steps.
 
@@ -126,34 +137,38 @@ class ArzRolloutFn(torch.autograd.Function):
         need_grad = any(ctx.needs_input_grad[i] for i in (0, 1, 3))
         S = (steps + K - 1) // K
         ckpt = None
+        # what the checkpoint buffer holds: the S states, and behind them the interface outcomes of every step where the
+        # kernels take them (ckpt_mode 1, include/dhts.h)
+        xmode, n = 0, S * 2 * B * N
+        if need_grad and not tv and not want_hist:
+            n, xmode = arz_ckpt_elems(B, N, steps, K, r0.dtype)
         if need_grad or want_hist:
-            n = S * 2 * B * N
             if ckpt_buffer is not None:      # caller-owned arena, reused across sequential rollouts (lane chunks)
                 if ckpt_buffer.dtype != r0.dtype or ckpt_buffer.device != dev or ckpt_buffer.numel() < n:
                     raise ValueError("ckpt_buffer must be a %s tensor on %s with >= %d elements" % (r0.dtype, dev, n))
-                ckpt = ckpt_buffer.view(-1)[:n].view(S, 2, B, N)
+                ckpt = ckpt_buffer.view(-1)[:n]
                 ctx.lease = _lease_arena(ckpt_buffer)
             else:
-                ckpt = torch.empty((S, 2, B, N), dtype=r0.dtype, device=dev)
+                ckpt = torch.empty((n,), dtype=r0.dtype, device=dev)
         rT = torch.empty_like(r0); yT = torch.empty_like(r0); uT = torch.empty_like(r0)
         with torch.cuda.device(dev):
             check(_fn("arz_rollout_fwd", r0.dtype)(ptr(r0), ptr(y0), ptr(u0), ptr(None if tv else ghost),
                                                    ptr(ghost if tv else None), ptr(dx), ptr(umax),
-                                                   creal(r0.dtype, dt_), B, N, steps, K, ptr(ckpt), ptr(rT), ptr(yT),
+                                                   creal(r0.dtype, dt_), B, N, steps, K, xmode, ptr(ckpt), ptr(rT), ptr(yT),
                                                    ptr(uT), ptr(flags), stream_ptr(dev)), "dhts_arz_rollout_fwd")
         if need_grad:
             ctx.save_for_backward(ckpt, u0, ghost, dx, umax, rT, yT)
         ctx.flags = flags
-        ctx.cfg = (dt_, steps, K, B, N, tv, bool(want_hist))
+        ctx.cfg = (dt_, steps, K, B, N, tv, bool(want_hist), xmode)
         if want_hist:
-            return rT, yT, uT, ckpt
+            return rT, yT, uT, ckpt.view(S, 2, B, N)
         return rT, yT, uT
 
     @staticmethod
     def backward(ctx, g_rT, g_yT, g_uT, g_hist=None):
         ckpt, u0, ghost, dx, umax, rT, yT = ctx.saved_tensors
         flags = ctx.flags
-        dt_, steps, K, B, N, tv, want_hist = ctx.cfg
+        dt_, steps, K, B, N, tv, want_hist, xmode = ctx.cfg
         dev, dtype = ghost.device, ghost.dtype
         g_rT, g_yT, g_uT, g_hist = map(_c, (g_rT, g_yT, g_uT, g_hist))
         g_r0 = torch.empty((B, N), dtype=dtype, device=dev)
@@ -165,7 +180,7 @@ class ArzRolloutFn(torch.autograd.Function):
                 raise _lib.UnsupportedShape("dhts_arz_rollout_bwd: lane does not fit the fused kernel")
             scratch = torch.empty((max(int(n), 1),), dtype=dtype, device=dev)
             check(_fn("arz_rollout_bwd", dtype)(ptr(ckpt), ptr(u0), ptr(None if tv else ghost), ptr(ghost if tv else None),
-                                                ptr(dx), ptr(umax), creal(dtype, dt_), B, N, steps, K, ptr(rT), ptr(yT),
+                                                ptr(dx), ptr(umax), creal(dtype, dt_), B, N, steps, K, xmode, ptr(rT), ptr(yT),
                                                 ptr(g_rT), ptr(g_yT), ptr(g_uT), ptr(g_hist), ptr(scratch),
                                                 ctypes.c_longlong(int(n)), ptr(g_r0), ptr(g_y0),
                                                 ptr(None if tv else g_gh), ptr(g_gh if tv else None), ptr(flags),

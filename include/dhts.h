@@ -99,8 +99,15 @@ int dhts_arz_step_bwd_f32(const float* r_pad, const float* y_pad, const float* u
  * own it for the whole rollout (1, 2, 4 or 8 consecutive cells per thread).
  *   r0, y0 [B][N]; u0 [B][N] or NULL (stored speed of the initial cells, set_r_u)
  *   ghost [B][2][3]        (r, y, u) of the left / right ghost cell
- *   ckpt [S][2][B][N] or NULL, S = ceil(steps/ckpt_every): state BEFORE steps
+ *   ckpt [S][2][B][N] (+ outcomes) or NULL, S = ceil(steps/ckpt_every): state BEFORE steps
  *                          0, K, 2K, ... (needed by the backward entry point)
+ *   ckpt_mode              0: ckpt holds the states only.  1: behind the S states it also holds the OUTCOME of every
+ *                          interface of every step (Q_L / Q_M / Q_C, _arz.py:324-336: two bits per interface, one
+ *                          halfword per thread and step), which lets the adjoint skip the Riemann case tree for half a
+ *                          byte per cell-step of HBM traffic.  dhts_arz_rollout_ckpt_elems_*(B, N, steps, ckpt_every,
+ *                          &mode) returns the elements `ckpt` must hold and the mode the kernels take for this shape
+ *                          (1 where every state is stored, the ghosts are static and the staged forward / ring adjoint
+ *                          kernels apply); callers pass that mode to both calls (0 is always accepted)
  *   rT, yT, uT [B][N]      final state, uT = compute_u(rT, yT)
  * Limits of the fused kernels: a lane must fit one CTA -- N <= 1024 cells in general (one or two cells per thread),
  * N <= 2048 when N is a multiple of 8 (256 threads x 8 cells; plan_reg in csrc/arz_rollout.cu) -- and with more than
@@ -111,16 +118,16 @@ int dhts_arz_step_bwd_f32(const float* r_pad, const float* y_pad, const float* u
  */
 int dhts_arz_rollout_fwd_f64(const double* r0, const double* y0, const double* u0, const double* ghost,
                              const double* ghost_t, const double* dx, const double* umax, double dt, int B, int N,
-                             int steps, int ckpt_every, double* ckpt, double* rT, double* yT, double* uT, int* flags,
-                             void* stream);
+                             int steps, int ckpt_every, int ckpt_mode, double* ckpt, double* rT, double* yT, double* uT,
+                             int* flags, void* stream);
 int dhts_arz_rollout_fwd_f32(const float* r0, const float* y0, const float* u0, const float* ghost,
                              const float* ghost_t, const float* dx, const float* umax, float dt, int B, int N,
-                             int steps, int ckpt_every, float* ckpt, float* rT, float* yT, float* uT, int* flags,
-                             void* stream);
+                             int steps, int ckpt_every, int ckpt_mode, float* ckpt, float* rT, float* yT, float* uT,
+                             int* flags, void* stream);
 
 /* Adjoint of the rollout: the chain of dMacroForwardLayer.backward calls autograd makes for the T steps
  * (road/lane/dmacro_lane.py:277-310), flux-difference form, no stored Jacobian band.
- *   ckpt                    what the forward call wrote (same ckpt_every)
+ *   ckpt                    what the forward call wrote (same ckpt_every, same ckpt_mode)
  *   rT, yT                  final state (only read when g_uT is given: uT = compute_u(rT, yT))
  *   g_rT, g_yT, g_uT [B][N] adjoint of the final state, each may be NULL
  *   scratch                 dhts_arz_rollout_scratch_elems(B, N, ckpt_every) elements (0 when ckpt_every = 1)
@@ -135,16 +142,18 @@ int dhts_arz_rollout_fwd_f32(const float* r0, const float* y0, const float* u0, 
  */
 int dhts_arz_rollout_bwd_f64(const double* ckpt, const double* u0, const double* ghost, const double* ghost_t,
                              const double* dx, const double* umax, double dt, int B, int N, int steps, int ckpt_every,
-                             const double* rT, const double* yT, const double* g_rT, const double* g_yT,
+                             int ckpt_mode, const double* rT, const double* yT, const double* g_rT, const double* g_yT,
                              const double* g_uT, const double* g_hist, double* scratch, long long scratch_elems,
                              double* g_r0, double* g_y0, double* g_ghost, double* g_ghost_t, int* flags, void* stream);
 int dhts_arz_rollout_bwd_f32(const float* ckpt, const float* u0, const float* ghost, const float* ghost_t,
                              const float* dx, const float* umax, float dt, int B, int N, int steps, int ckpt_every,
-                             const float* rT, const float* yT, const float* g_rT, const float* g_yT, const float* g_uT,
+                             int ckpt_mode, const float* rT, const float* yT, const float* g_rT, const float* g_yT, const float* g_uT,
                              const float* g_hist, float* scratch, long long scratch_elems, float* g_r0, float* g_y0,
                              float* g_ghost, float* g_ghost_t, int* flags, void* stream);
 long long dhts_arz_rollout_scratch_elems_f64(int B, int N, int ckpt_every);
 long long dhts_arz_rollout_scratch_elems_f32(int B, int N, int ckpt_every);
+long long dhts_arz_rollout_ckpt_elems_f64(int B, int N, int steps, int ckpt_every, int* ckpt_mode);
+long long dhts_arz_rollout_ckpt_elems_f32(int B, int N, int steps, int ckpt_every, int* ckpt_mode);
 
 /* ---------------------------------------------------------------- IDM, one step
  * Forward half of dMicroForwardLayer (dmicro_lane.py:230-269 -> MicroLane.forward,

@@ -249,7 +249,9 @@ def test_rollout_cfl_slow_path_and_arena_and_unaligned(dev):
     w = rng.normal(size=(B, N))
     o = O.arz_rollout(r0, u0, gh, dx, umax, dt, T, g_rT=w, g_uT=w / umax)
     assert o["cfl"] == 0
-    arena = torch.empty(T * 2 * B * N + 5, dtype=torch.float64, device=dev)
+    n_ck = F.arz_ckpt_elems(B, N, T, 1, torch.float64)      # the T states and, where stored, the interface outcomes
+    assert n_ck >= T * 2 * B * N
+    arena = torch.empty(n_ck + 5, dtype=torch.float64, device=dev)
     for mode in ("plain", "arena", "unaligned"):
         flags = dhts_b200.Flags(dev)
         if mode == "unaligned":

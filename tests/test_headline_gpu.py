@@ -33,7 +33,7 @@ def test_arz_headline_modes_vs_oracle(dev):
     d = {k: v.to(dev) for k, v in dict(r0=r0, u0=u0, gr=gr, gu=gu, tr=tr, tu=tu).items()}
     flags = dhts_b200.Flags(dev)
     chunk = B // 2
-    arena = torch.empty(T * 2 * chunk * N, dtype=torch.float64, device=dev)     # one arena, reused by both chunks
+    arena = torch.empty(F.arz_ckpt_elems(chunk, N, T, 1, torch.float64), dtype=torch.float64, device=dev)     # one arena (states + interface outcomes), reused by both chunks
 
     def run(K, chunks, arena):
         out = {k: torch.empty((B, N), dtype=torch.float64, device=dev) for k in ("rT", "uT", "g_r0", "g_u0")}
