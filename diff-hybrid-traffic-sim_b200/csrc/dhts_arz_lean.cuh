@@ -87,16 +87,18 @@ __device__ __forceinline__ FRec<T> fderive(T r, T y, T us_in, const LaneK<T>& k)
     const T ri = rs * rs;
     const T se = f_sqrt_pos(rc + DHTS_EPS);
     const T ueqc = fma(-k.umax, se, k.umax);           // u_eq at the clamped r (compute_u, _arz.py:126-131)
-    const T yri = y * ri;
-    const T uc = yri + ueqc;
+    // every multiply-add of the step is an EXPLICIT fma (or has no product feeding a sum): the compiler's own contraction
+    // differs between the kernels this is inlined into, and the segment recompute of the adjoint must reproduce the
+    // forward kernel's states bit for bit (tests/test_fullsize_gpu.py: gradients do not depend on ckpt_every)
+    const T uc = fma(y, ri, ueqc);
     c.r = r; c.sq = rc * rs;
     c.us = STORED ? us_in : uc;
-    c.w = STORED ? (k.umax + us_in - ueqc) : (k.umax + yri);     // u_max + u - u_eq(r)
+    c.w = STORED ? ((k.umax + us_in) - ueqc) : fma(y, ri, k.umax);   // u_max + u - u_eq(r)
     c.fr = r * uc; c.fy = y * uc;                       // Q_L re-derives u from (r, y), _arz.py:155-165
     return c;
 }
 template <typename T> __device__ __forceinline__ T w_vacuum(T r, T us, const LaneK<T>& k) {
-    return k.umax + us - k.umax * (T(1) - f_sqrt_pos(t_max(r, T(0)) + DHTS_EPS));
+    return fma(-k.umax, T(1) - f_sqrt_pos(t_max(r, T(0)) + DHTS_EPS), k.umax + us);
 }
 
 // Outcome predicates of the case tree (_arz.py:225-322), shared by forward and adjoint.
@@ -156,7 +158,7 @@ __device__ __forceinline__ void fflux(const FRec<T>& L, T Rr, T Rus, const LaneK
     const T root = t.isM ? t.b : t.q;
     const T r0 = root * root;
     const T u0 = t.isM ? Rus : t.sc * (T(0.5) / T(1.5));
-    const T ueq = fma(-k.umax, f_sqrt_pos(r0 + DHTS_EPS), k.umax);
+    const T ueq = fma(-k.umax, f_sqrt_pos(fma(root, root, DHTS_EPS)), k.umax);
     const T y0 = r0 * (u0 - ueq);
     fr = t.isL ? L.fr : r0 * u0;
     fy = t.isL ? L.fy : y0 * u0;
@@ -172,7 +174,7 @@ __device__ __forceinline__ void fflux_x(const FRec<T>& L, T Rr, T Rus, const Lan
     const T root = t.isM ? t.b : t.q;
     const T r0 = root * root;
     const T u0 = t.isM ? Rus : t.sc * (T(0.5) / T(1.5));
-    const T ueq = fma(-k.umax, f_sqrt_pos(r0 + DHTS_EPS), k.umax);
+    const T ueq = fma(-k.umax, f_sqrt_pos(fma(root, root, DHTS_EPS)), k.umax);
     const T y0 = r0 * (u0 - ueq);
     fr = t.isL ? L.fr : r0 * u0;
     fy = t.isL ? L.fy : y0 * u0;
@@ -205,8 +207,8 @@ __device__ __forceinline__ ARec<T> aderive(T r, T y, T us_in, const LaneK<T>& k)
     const T uf = fma(-k.umax, se, k.umax);
     const T yri = y * ri;
     c.r = r; c.sq = rc * rs; c.ri = ri;
-    c.us = STORED ? us_in : (yri + uf);
-    c.w = STORED ? (k.umax + us_in - uf) : (k.umax + yri);
+    c.us = STORED ? us_in : fma(y, ri, uf);              // bitwise the forward record (fderive)
+    c.w = STORED ? ((k.umax + us_in) - uf) : fma(y, ri, k.umax);
     c.ueqp = -k.hum * rs;                               // u_eq'(max(r,eps)), _arz.py:146-149
     c.plr = -yri * ri;
     c.f00 = fma(rc, c.ueqp, uf);                        // flux_prime at (r, y) with the fresh u_eq(r), darz.py:217-233
@@ -216,8 +218,9 @@ __device__ __forceinline__ ARec<T> aderive(T r, T y, T us_in, const LaneK<T>& k)
 }
 // r < eps: the fresh u_eq(r) enters w, f00 and f11 (the clamped one stays in us)
 template <typename T> __device__ __forceinline__ void fix_vacuum_adj(ARec<T>& c, T y, const LaneK<T>& k) {
-    const T uf = k.umax * (T(1) - f_sqrt_pos(t_max(c.r, T(0)) + DHTS_EPS));
-    c.w = k.umax + c.us - uf;
+    const T om = T(1) - f_sqrt_pos(t_max(c.r, T(0)) + DHTS_EPS);
+    const T uf = k.umax * om;
+    c.w = fma(-k.umax, om, k.umax + c.us);              // bitwise w_vacuum
     c.f00 = fma(DHTS_EPS, c.ueqp, uf);
     c.f11 = fma(T(2), y * c.ri, uf);
 }
@@ -231,7 +234,7 @@ __device__ __forceinline__ void aflux(const ARec<T>& L, const ARec<T>& R, T wr, 
     const T r0 = root * root;
     const T rootr = t_abs(root);
     const T u0 = t.isM ? R.us : t.sc * (T(0.5) / T(1.5));
-    const T ueq0 = fma(-k.umax, f_sqrt_pos(r0 + DHTS_EPS), k.umax);
+    const T ueq0 = fma(-k.umax, f_sqrt_pos(fma(root, root, DHTS_EPS)), k.umax);
     const T g = u0 - ueq0;
     const T y0 = r0 * g;
     // flux_prime at Q0 with r clamped at eps
@@ -274,7 +277,7 @@ __device__ __forceinline__ void aflux_x(const ARec<T>& L, const ARec<T>& R, T wr
     const T r0 = root * root;
     const T rootr = t_abs(root);
     const T u0 = isM ? R.us : sc * (T(0.5) / T(1.5));
-    const T ueq0 = fma(-k.umax, f_sqrt_pos(r0 + DHTS_EPS), k.umax);
+    const T ueq0 = fma(-k.umax, f_sqrt_pos(fma(root, root, DHTS_EPS)), k.umax);
     const T g = u0 - ueq0;
     const T y0 = r0 * g;
     const bool big = r0 >= DHTS_EPS;
