@@ -255,18 +255,24 @@ __device__ __forceinline__ FRec<T> fcell(T r, T y, T us, const LaneK<T>& k) {
     return c;
 }
 
-// XR: also collect the outcome of every interface (dhts_arz_lean.cuh): two bits per interface, the one on the left of cell c
-// at bits 2c, 2c + 1 of `ob` -- one halfword per thread and step, which the adjoint (same thread -> cell mapping) reads back.
+// XR: also store the outcome of every interface (dhts_arz_lean.cuh) as warp BALLOTS: for the interface on the left of cell c
+// of every thread of the warp, xs[c] = (ballot of Q_L, ballot of Q_M) -- one vote per bit and one 8-byte store by lane 0
+// instead of per-thread bit assembly; the adjoint (same thread -> cell mapping) tests its lane's bit.
 template <typename T, int C, bool STORED, bool CHECK, bool VAC, bool XR>
 __device__ __forceinline__ bool chunk_fwd_sweep(T* r, T* y, const T* us, const FRec<T>& last, FRec<T>& L,
-                                                const LaneK<T>& k, T dt, T* f0, T& fpr, T& fpy, bool& okL, unsigned& ob) {
+                                                const LaneK<T>& k, T dt, T* f0, T& fpr, T& fpy, bool& okL, uint2* xs,
+                                                unsigned lane) {
     bool bad = false;
 #pragma unroll
     for (int c = 0; c < C; c++) {
         const FRec<T> cur = (c == C - 1) ? last : fcell<T, STORED, VAC>(r[c], y[c], STORED ? us[c] : T(0), k);
         T fr, fy;
-        if (XR) { unsigned b2; fflux_x<T, VAC>(L, cur.r, cur.us, k, fr, fy, b2); ob |= b2 << (2 * c); }
-        else fflux<T, VAC>(L, cur.r, cur.us, k, fr, fy);
+        if (XR) {
+            bool isL, isM;
+            fflux_x<T, VAC>(L, cur.r, cur.us, k, fr, fy, isL, isM);
+            const unsigned bL = __ballot_sync(FULL, isL), bM = __ballot_sync(FULL, isM);
+            if (lane == 0) xs[c] = make_uint2(bL, bM);
+        } else fflux<T, VAC>(L, cur.r, cur.us, k, fr, fy);
         if (CHECK) {
             const bool okR = cell_speed_ok(cur.us, cur.w, k);
             // never in a valid run; the vote makes the branch warp-uniform (no reconvergence bookkeeping around it): every
@@ -284,11 +290,11 @@ __device__ __forceinline__ bool chunk_fwd_sweep(T* r, T* y, const T* us, const F
     return bad;
 }
 
-// sx (XR): where this thread's outcome halfword of the step goes in the staging ring (null: inactive thread / not stored).
+// xs (XR): the C outcome ballot pairs of this thread's WARP in the step's stage of the staging ring.
 template <typename T, int C, bool STORED, bool CHECK, bool XR = false>
 __device__ __forceinline__ bool chunk_fwd_step(T* r, T* y, const T* us, bool first_chunk, bool last_chunk,
                                                const LaneK<T>& k, const T* ghostL, const T* ghostR, T dt, T* boxL,
-                                               T* boxR, int warp, int nwarp, unsigned lane, unsigned short* sx = nullptr) {
+                                               T* boxR, int warp, int nwarp, unsigned lane, uint2* xs = nullptr) {
     const FRec<T> last = fcell<T, STORED, true>(r[C - 1], y[C - 1], STORED ? us[C - 1] : T(0), k);
     T mine[RF_FWD], left[RF_FWD];
     pack(last, mine);
@@ -301,15 +307,11 @@ __device__ __forceinline__ bool chunk_fwd_step(T* r, T* y, const T* us, bool fir
     T f0[2], fpr = T(0), fpy = T(0);
     bool bad;
     anyvac = __any_sync(FULL, anyvac);            // one variant per warp (a mixed warp would run both, one after the other)
-    unsigned ob = 0;
-    if (__builtin_expect(anyvac, 0)) bad = chunk_fwd_sweep<T, C, STORED, CHECK, true, XR>(r, y, us, last, L, k, dt, f0, fpr, fpy, okL, ob);
-    else bad = chunk_fwd_sweep<T, C, STORED, CHECK, false, XR>(r, y, us, last, L, k, dt, f0, fpr, fpy, okL, ob);
-    // (XR) the outcomes go into the step's stage; this fence -- before the step's second block barrier, after which the bulk
+    if (__builtin_expect(anyvac, 0)) bad = chunk_fwd_sweep<T, C, STORED, CHECK, true, XR>(r, y, us, last, L, k, dt, f0, fpr, fpy, okL, xs, lane);
+    else bad = chunk_fwd_sweep<T, C, STORED, CHECK, false, XR>(r, y, us, last, L, k, dt, f0, fpr, fpy, okL, xs, lane);
+    // (XR) the outcomes went into the step's stage; this fence -- before the step's second block barrier, after which the bulk
     // store is issued -- also covers the (r, y) rows written at the top of the step
-    if (XR) {
-        if (sx) *sx = (unsigned short)ob;
-        fence_proxy_async();
-    }
+    if (XR) fence_proxy_async();
     T fR[2];
     from_right<T, 2>(f0, fR, boxR, warp, nwarp, lane);
     if (last_chunk) {   // interface with the right ghost cell
@@ -330,24 +332,44 @@ __device__ __forceinline__ bool chunk_fwd_step(T* r, T* y, const T* us, bool fir
 // XR (staged mode only): besides (r, y) every state stores the OUTCOME of each interface of the step taken from it -- one
 // halfword per thread, behind the states in `ckpt` -- which lets the adjoint skip the case tree (aflux_x) for half a byte
 // per cell-step of HBM traffic.
-template <typename T> __host__ __device__ inline size_t xrow_elems(int lpc, int tpl) {      // outcome row of a stage, in elements
-    return (((size_t)lpc * tpl * 2 + 15) / 16 * 16) / sizeof(T);
+// Outcome rows: C ballot pairs (8 bytes each) per warp and step, i.e. tpl / 32 * C * 8 = N / 4 bytes per lane and step.
+__host__ __device__ inline size_t xlane_bytes(int tpl, int C) { return (size_t)(tpl / 32) * C * 8; }
+template <typename T> __host__ __device__ inline size_t xrow_elems(int lpc, int tpl, int C) {      // outcome row of a stage, in elements
+    return (((size_t)lpc * xlane_bytes(tpl, C) + 15) / 16 * 16) / sizeof(T);
 }
+// Launch constants of the staged / ring paths, computed once on the host: as kernel parameters they sit in the constant bank
+// and cost no instruction where they are used (the step loops re-derived them every step before: ~10 % of the adjoint's
+// instructions were 64-bit index arithmetic).
+struct RollK {
+    int stage_elems;          // one stage of the ring: (r, y) rows of the CTA's lanes + outcome row, in elements
+    int y_off, x_off;         // the y rows / the outcome row inside a stage, in elements
+    int ring_off;             // byte offset of the ring in the CTA's dynamic shared memory
+    long long step_stride;    // 2 B N: one stored state, in elements
+    long long x_stride;       // B x xlane_bytes: the outcome rows of one step, in bytes
+};
+template <typename T> static RollK make_rollk(int B, int N, int C, int lpc, int nwarp, bool fwd, bool xr) {
+    RollK k;
+    k.y_off = lpc * N; k.x_off = 2 * lpc * N;
+    k.stage_elems = 2 * lpc * N + (xr ? (int)xrow_elems<T>(lpc, N / C, C) : 0);
+    k.ring_off = (int)ring_offset<T>(lpc, nwarp, fwd);
+    k.step_stride = 2LL * B * N;
+    k.x_stride = (long long)B * (long long)xlane_bytes(N / C, C);
+    return k;
+}
+
 template <typename T, int C, int MB, int NS, bool TV = false, bool XR = false>
 __global__ void __launch_bounds__(1024 / (C < 4 ? C : 4), MB) arz_rollout_fwd_reg_kernel(const T* __restrict__ r0, const T* __restrict__ y0,
                                            const T* __restrict__ u0, const T* __restrict__ ghost,
                                            const T* __restrict__ ghost_t,
                                            const T* __restrict__ dx, const T* __restrict__ umax_, T dt, int B, int N,
-                                           int steps, int K, int lpc, T* __restrict__ ckpt, T* __restrict__ rT,
+                                           int steps, int K, int lpc, const RollK rk, T* __restrict__ ckpt, T* __restrict__ rT,
                                            T* __restrict__ yT, T* __restrict__ uT, int* __restrict__ flags) {
     extern __shared__ __align__(128) unsigned char raw[];
     const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5;
     const unsigned lane = threadIdx.x & 31;
     Shm<T> s = carve_shm<T>(raw, lpc, nwarp, true);
     const int tpl = N / C;                        // threads per lane
-    const size_t stage_elems = (size_t)2 * lpc * N + (XR ? xrow_elems<T>(lpc, tpl) : 0);
-    T* stg = reinterpret_cast<T*>(raw + ring_offset<T>(lpc, nwarp, true));     // [NS][(r, y) x lpc * N | outcomes]
-    int stg_i = 0;
+    T* stg = reinterpret_cast<T*>(raw + rk.ring_off);     // [NS][(r, y) x lpc * N | outcomes]
     const int l = threadIdx.x / tpl, kc = threadIdx.x - l * tpl;
     const int ngroup = (B + lpc - 1) / lpc;
     bool bad = false;
@@ -377,6 +399,46 @@ __global__ void __launch_bounds__(1024 / (C < 4 ? C : 4), MB) arz_rollout_fwd_re
         T* ckrow = ckpt ? ckpt + (size_t)lane0 * N : nullptr;      // same, start of the group's rows (bulk stores)
         const unsigned rowbytes = (unsigned)((size_t)nl * N * sizeof(T));
         int next_ck = 0;
+        if (NS > 0) {
+            // Staged path (every state stored, K == 1): running pointers into the staging ring and into `ckpt`, advanced by the
+            // launch constants; step 0 (explicitly stored speeds) is peeled so that the loop holds ONE copy of the step.
+            T* sp = stg + soff;                                    // this thread's r chunk in the current stage
+            uint2* sx = XR ? reinterpret_cast<uint2*>(stg + rk.x_off) + warp * C : nullptr;     // this warp's ballots, same stage
+            unsigned char* xrow = XR ? reinterpret_cast<unsigned char*>(ckpt + (size_t)steps * rk.step_stride) + (size_t)lane0 * xlane_bytes(tpl, C) : nullptr;
+            const unsigned xbytes = (unsigned)((size_t)nl * xlane_bytes(tpl, C));
+            int stg_i = 0;
+            T* bl = s.boxL; T* br = s.boxR;
+            int flipl = nwarp * RF_FWD, flipr = nwarp * 4;
+            for (int t = 0; t < steps; t++) {
+                // Stage t % NS is free: its previous bulk store (step t - NS) was waited for by thread 0 at the top of step
+                // t - 1, before that step's block barriers.
+                if (active) { store_chunk<T, C>(sp, r); store_chunk<T, C>(sp + rk.y_off, y); }
+                if (!XR) fence_proxy_async();
+                if (threadIdx.x == 0) bulk_wait_read<(NS > 2 ? NS - 2 : 0)>();
+                if (t == 0 && u0) {
+                    T us[C];
+                    load_chunk<T, C>(u0 + off, us);
+                    lbad |= chunk_fwd_step<T, C, true, true, XR>(r, y, us, first_chunk, last_chunk, k, gL, gR, dt, bl, br, warp, nwarp, lane, sx);
+                } else
+                    lbad |= chunk_fwd_step<T, C, false, true, XR>(r, y, nullptr, first_chunk, last_chunk, k, gL, gR, dt, bl, br, warp, nwarp, lane, sx);
+                bl += flipl; flipl = -flipl; br += flipr; flipr = -flipr;
+                // every thread has passed the step's block barriers: the stage is complete and fenced
+                if (threadIdx.x == 0) {     // thread 0: soff == 0, sp is the stage
+                    bulk_s2g(ckrow, sp, rowbytes);
+                    bulk_s2g(ckrow + BN, sp + rk.y_off, rowbytes);
+                    if (XR) bulk_s2g(xrow, sp + rk.x_off, xbytes);      // outcome ballots: behind the `steps` stored states
+                    bulk_commit();
+                }
+                ckrow += rk.step_stride;
+                if (XR) { xrow += rk.x_stride; sx += (size_t)rk.stage_elems * sizeof(T) / sizeof(uint2); }
+                sp += rk.stage_elems;
+                if (++stg_i == NS) {
+                    stg_i = 0; sp -= (size_t)NS * rk.stage_elems;
+                    if (XR) sx -= (size_t)NS * rk.stage_elems * sizeof(T) / sizeof(uint2);
+                }
+            }
+            if (threadIdx.x == 0) bulk_wait_read<0>();      // stages are rewritten by the next lane group
+        } else
         for (int t = 0; t < steps; t++) {
             if (TV) {       // this step's ghost records (published by the step's first block barrier), then prefetch the next ones
                 if (gthread) {
@@ -385,47 +447,19 @@ __global__ void __launch_bounds__(1024 / (C < 4 ? C : 4), MB) arz_rollout_fwd_re
                 }
                 gL = s.ghostF + ((size_t)(t & 1) * lpc * 2 + ll * 2) * GH_F; gR = gL + GH_F;
             }
-            const bool store_now = ck && t == next_ck;
-            if (store_now) {
-                if (NS > 0) {
-                    // Stage t % NS is free: its previous bulk store (step t - NS) was waited for by thread 0 at the
-                    // top of step t - 1, before that step's block barriers.
-                    T* sp = stg + (size_t)stg_i * stage_elems + soff;
-                    if (active) { store_chunk<T, C>(sp, r); store_chunk<T, C>(sp + (size_t)lpc * N, y); }
-                    if (!XR) fence_proxy_async();
-                    if (threadIdx.x == 0) bulk_wait_read<(NS > 2 ? NS - 2 : 0)>();
-                } else {
-                    if (active) { store_chunk<T, C>(ck, r); store_chunk<T, C>(ck + BN, y); }
-                    ck += 2 * BN;
-                }
+            if (ck && t == next_ck) {
+                if (active) { store_chunk<T, C>(ck, r); store_chunk<T, C>(ck + BN, y); }
+                ck += 2 * BN;
                 next_ck += K;
             }
-            unsigned short* sx = (XR && store_now && active)
-                                     ? reinterpret_cast<unsigned short*>(stg + (size_t)stg_i * stage_elems + (size_t)2 * lpc * N) + ll * tpl + kc
-                                     : nullptr;
             if (t == 0 && u0) {
                 T us[C];
                 load_chunk<T, C>(u0 + off, us);
-                lbad |= chunk_fwd_step<T, C, true, true, XR>(r, y, us, first_chunk, last_chunk, k, gL, gR, dt, blA, brA, warp, nwarp, lane, sx);
+                lbad |= chunk_fwd_step<T, C, true, true>(r, y, us, first_chunk, last_chunk, k, gL, gR, dt, blA, brA, warp, nwarp, lane);
             } else
-                lbad |= chunk_fwd_step<T, C, false, true, XR>(r, y, nullptr, first_chunk, last_chunk, k, gL, gR, dt, blA, brA, warp, nwarp, lane, sx);
+                lbad |= chunk_fwd_step<T, C, false, true>(r, y, nullptr, first_chunk, last_chunk, k, gL, gR, dt, blA, brA, warp, nwarp, lane);
             T* x = blA; blA = blB; blB = x; x = brA; brA = brB; brB = x;
-            if (NS > 0 && store_now) {
-                // every thread has passed the step's block barriers: the stage is complete and fenced
-                if (threadIdx.x == 0) {
-                    const T* sp = stg + (size_t)stg_i * stage_elems;
-                    bulk_s2g(ckrow, sp, rowbytes);
-                    bulk_s2g(ckrow + BN, sp + (size_t)lpc * N, rowbytes);
-                    if (XR)      // outcome halfwords of the group's lanes: behind the `steps` stored states
-                        bulk_s2g(reinterpret_cast<unsigned short*>(ckpt + (size_t)steps * 2 * BN) + ((size_t)t * B + lane0) * tpl,
-                                 sp + (size_t)2 * lpc * N, (unsigned)((size_t)nl * tpl * 2));
-                    bulk_commit();
-                }
-                ckrow += 2 * BN;
-                if (++stg_i == NS) stg_i = 0;
-            }
         }
-        if (NS > 0 && threadIdx.x == 0) bulk_wait_read<0>();      // stages are rewritten by the next lane group
         bad |= lbad && active;
         if (active) {
             T u[C];
@@ -451,18 +485,19 @@ __device__ __forceinline__ ARec<T> acell(T r, T y, T us, const LaneK<T>& k) {
     return c;
 }
 
-// XR: the forward pass stored the outcome of every interface (bits 2c, 2c + 1 of ob: interface on the left of cell c) -> aflux_x.
+// XR: the forward pass stored the outcome of every interface (xs[c]: warp ballots of Q_L / Q_M for the interface on the left
+// of cell c; lm = this lane's bit) -> aflux_x.
 template <typename T, int C, bool STORED, bool VAC, bool XR>
 __device__ __forceinline__ bool chunk_adj_sweep(const T* r, const T* y, const T* us, T* gr, T* gy, const ARec<T>& last,
                                                 ARec<T>& L, T& gLr, T& gLy, const LaneK<T>& k, T* a0, T& bpr, T& bpy,
-                                                unsigned ob) {
+                                                const uint2* xs, unsigned lm) {
     bool nan = false;
 #pragma unroll
     for (int c = 0; c < C; c++) {
         const ARec<T> cur = (c == C - 1) ? last : acell<T, STORED, VAC>(r[c], y[c], STORED ? us[c] : T(0), k);
         const T gcr = gr[c], gcy = gy[c];
         T ar, ay, br, by;
-        if (XR) aflux_x<T>(L, cur, gcr - gLr, gcy - gLy, k, ob >> (2 * c), ar, ay, br, by);
+        if (XR) { const uint2 w = xs[c]; aflux_x<T>(L, cur, gcr - gLr, gcy - gLy, k, (w.x & lm) != 0, (w.y & lm) != 0, ar, ay, br, by); }
         else aflux<T, VAC>(L, cur, gcr - gLr, gcy - gLy, k, ar, ay, br, by);
         if (c == 0) { a0[0] = ar; a0[1] = ay; }
         else {
@@ -478,7 +513,7 @@ template <typename T, int C, bool STORED, bool XR = false>
 __device__ __forceinline__ bool chunk_adj_step(const T* r, const T* y, const T* us, T* gr, T* gy, bool first_chunk,
                                                bool last_chunk, const LaneK<T>& k, const T* ghostL, const T* ghostR,
                                                T* accL, T* accR, T* boxL, T* boxR, int warp, int nwarp, unsigned lane,
-                                               unsigned ob = 0) {
+                                               const uint2* xs = nullptr) {
     const T rl = r[C - 1];
     const ARec<T> last = acell<T, STORED, true>(rl, y[C - 1], STORED ? us[C - 1] : T(0), k);
     constexpr int NF = XR ? RF_ADJX : RF_ADJ;     // the stored-outcome path hands over a shorter record (no r, no w)
@@ -488,13 +523,16 @@ __device__ __forceinline__ bool chunk_adj_step(const T* r, const T* y, const T* 
     ARec<T> L = first_chunk ? unpack_a(ghostL) : (XR ? unpack_x(left) : unpack_a(left));
     T gLr = first_chunk ? T(0) : left[NF - 2], gLy = first_chunk ? T(0) : left[NF - 1];   // OLD adjoint of the cell on the left
     T a0[2], bpr = T(0), bpy = T(0);
-    bool anyvac = maybe_vac(L.r) || maybe_vac(rl);
+    // XR: the sweep variants differ only in how the thread's own cells 0 .. C-2 are derived (the hand-over record carries no r,
+    // the last cell is always derived with the vacuum handling)
+    bool anyvac = XR ? false : (maybe_vac(L.r) || maybe_vac(rl));
 #pragma unroll
     for (int c = 0; c < C - 1; c++) anyvac |= maybe_vac(r[c]);
     bool nan;
     anyvac = __any_sync(FULL, anyvac);            // one variant per warp
-    if (__builtin_expect(anyvac, 0)) nan = chunk_adj_sweep<T, C, STORED, true, XR>(r, y, us, gr, gy, last, L, gLr, gLy, k, a0, bpr, bpy, ob);
-    else nan = chunk_adj_sweep<T, C, STORED, false, XR>(r, y, us, gr, gy, last, L, gLr, gLy, k, a0, bpr, bpy, ob);
+    const unsigned lm = 1u << lane;
+    if (__builtin_expect(anyvac, 0)) nan = chunk_adj_sweep<T, C, STORED, true, XR>(r, y, us, gr, gy, last, L, gLr, gLy, k, a0, bpr, bpy, xs, lm);
+    else nan = chunk_adj_sweep<T, C, STORED, false, XR>(r, y, us, gr, gy, last, L, gLr, gLy, k, a0, bpr, bpy, xs, lm);
     T aR[2];
     from_right<T, 2>(a0, aR, boxR, warp, nwarp, lane);
     if (last_chunk) {   // interface with the right ghost (its updated-state adjoint is zero)
@@ -525,16 +563,15 @@ __global__ void __launch_bounds__(1024 / (C < 4 ? C : 4), MB) arz_rollout_bwd_re
                                            const T* __restrict__ g_rT, const T* __restrict__ g_yT,
                                            const T* __restrict__ g_uT, T* __restrict__ scratch,
                                            T* __restrict__ g_r0, T* __restrict__ g_y0, T* __restrict__ g_ghost,
-                                           int* __restrict__ flags, int ring_ns) {
+                                           int* __restrict__ flags, int ring_ns, const RollK rk) {
     extern __shared__ __align__(128) unsigned char raw[];
     const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5;
     const unsigned lane = threadIdx.x & 31;
     Shm<T> s = carve_shm<T>(raw, lpc, nwarp);
     // state ring of the every-state-stored adjoint: ring_ns stages of (r row, y row) of the CTA's lanes, filled by
     // TMA bulk copies that complete on one mbarrier per stage
-    const size_t stage_elems = (size_t)2 * lpc * N + (XR ? xrow_elems<T>(lpc, N / C) : 0);
-    T* ring = reinterpret_cast<T*>(raw + ring_offset<T>(lpc, nwarp));
-    uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)ring_ns * stage_elems);
+    T* ring = reinterpret_cast<T*>(raw + rk.ring_off);
+    uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)ring_ns * rk.stage_elems);
     if (MODE == 0) {
         if (threadIdx.x == 0) {
             for (int i = 0; i < ring_ns; i++) mbar_init(full + i, 1);
@@ -585,40 +622,51 @@ __global__ void __launch_bounds__(1024 / (C < 4 ? C : 4), MB) arz_rollout_bwd_re
             // the shared-memory ring, ring_ns steps ahead of the arithmetic.  A stage is refilled at the top of the
             // step after the one that consumed it: by then every thread has passed that step's two block barriers,
             // i.e. has finished reading the stage.
+            // Running pointers advanced by the launch constants (RollK) instead of per-step index arithmetic.
             const unsigned rowbytes = (unsigned)((size_t)nl * N * sizeof(T));
-            const unsigned xbytes = (unsigned)((size_t)nl * tpl * 2);
-            const T* src0 = ckpt + (size_t)lane0 * N;
-            const unsigned short* xg0 = reinterpret_cast<const unsigned short*>(ckpt + (size_t)steps * 2 * BN) + (size_t)lane0 * tpl;
+            const unsigned xbytes = (unsigned)((size_t)nl * xlane_bytes(tpl, C));
+            const T* src = ckpt + (size_t)lane0 * N + (size_t)(steps > 0 ? steps - 1 : 0) * rk.step_stride;      // next state to fetch (thread 0)
+            const unsigned char* xsrc = reinterpret_cast<const unsigned char*>(ckpt + (size_t)steps * rk.step_stride) +
+                                        (size_t)lane0 * xlane_bytes(tpl, C) + (size_t)(steps > 0 ? steps - 1 : 0) * rk.x_stride;
             int issued = 0;
 #define DHTS_RING_ISSUE                                                                                  \
             {                                                                                            \
                 uint64_t* bar_ = full + fill_st;                                                         \
-                T* dst_ = ring + (size_t)fill_st * stage_elems;                                          \
-                const T* src_ = src0 + (size_t)(steps - 1 - issued) * 2 * BN;                            \
+                T* dst_ = ring + (size_t)fill_st * rk.stage_elems;                                       \
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                             \
                 mbar_expect_tx(bar_, 2 * rowbytes + (XR ? xbytes : 0u));                                 \
-                bulk_g2s(dst_, src_, rowbytes, bar_);                                                    \
-                bulk_g2s(dst_ + (size_t)lpc * N, src_ + BN, rowbytes, bar_);                             \
-                if (XR) bulk_g2s(dst_ + (size_t)2 * lpc * N, xg0 + (size_t)(steps - 1 - issued) * B * tpl, xbytes, bar_); \
+                bulk_g2s(dst_, src, rowbytes, bar_);                                                     \
+                bulk_g2s(dst_ + rk.y_off, src + BN, rowbytes, bar_);                                     \
+                if (XR) bulk_g2s(dst_ + rk.x_off, xsrc, xbytes, bar_);                                   \
+                src -= rk.step_stride; xsrc -= rk.x_stride;                                              \
                 issued++;                                                                                \
                 if (++fill_st == ring_ns) fill_st = 0;                                                   \
             }
             if (threadIdx.x == 0)
                 while (issued < ring_ns && issued < steps) DHTS_RING_ISSUE
+            const T* rp = ring + (size_t)use_st * rk.stage_elems + soff;        // this thread's r chunk in the stage to consume
+            const uint2* xp = XR ? reinterpret_cast<const uint2*>(ring + (size_t)use_st * rk.stage_elems + rk.x_off) + warp * C : nullptr;
+            T* bl = s.boxL; T* br = s.boxR;
+            int flipl = nwarp * RF_ADJ, flipr = nwarp * 4;
             for (int t = steps - 1; t >= 0; t--) {
                 if (threadIdx.x == 0 && t != steps - 1 && issued < steps) DHTS_RING_ISSUE
                 mbar_wait(full + use_st, use_par);
                 // cells are read from the stage where the sweep needs them (no register copy of the chunk); the
                 // last read precedes the step's second block barrier
-                const T* r = ring + (size_t)use_st * stage_elems + soff;
-                const T* y = r + (size_t)lpc * N;
-                const unsigned ob = XR ? reinterpret_cast<const unsigned short*>(ring + (size_t)use_st * stage_elems + (size_t)2 * lpc * N)[ll * tpl + kc] : 0u;
-                if (++use_st == ring_ns) { use_st = 0; use_par ^= 1u; }
+                const T* r = rp;
+                const T* y = rp + rk.y_off;
+                const uint2* ob = xp;
+                rp += rk.stage_elems;
+                if (XR) xp += (size_t)rk.stage_elems * sizeof(T) / sizeof(uint2);
+                if (++use_st == ring_ns) {
+                    use_st = 0; use_par ^= 1u; rp -= (size_t)ring_ns * rk.stage_elems;
+                    if (XR) xp -= (size_t)ring_ns * rk.stage_elems * sizeof(T) / sizeof(uint2);
+                }
                 if (t == 0 && u0)
-                    { T us_[C]; load_chunk<T, C>(u0 + off, us_); nan |= chunk_adj_step<T, C, true, XR>(r, y, us_, gr, gy, first_chunk, last_chunk, k, gLa, gRa, accL, accR, blA, brA, warp, nwarp, lane, ob); }
+                    { T us_[C]; load_chunk<T, C>(u0 + off, us_); nan |= chunk_adj_step<T, C, true, XR>(r, y, us_, gr, gy, first_chunk, last_chunk, k, gLa, gRa, accL, accR, bl, br, warp, nwarp, lane, ob); }
                 else
-                    nan |= chunk_adj_step<T, C, false, XR>(r, y, nullptr, gr, gy, first_chunk, last_chunk, k, gLa, gRa, accL, accR, blA, brA, warp, nwarp, lane, ob);
-                DHTS_SWAP_BOXES
+                    nan |= chunk_adj_step<T, C, false, XR>(r, y, nullptr, gr, gy, first_chunk, last_chunk, k, gLa, gRa, accL, accR, bl, br, warp, nwarp, lane, ob);
+                bl += flipl; flipl = -flipl; br += flipr; flipr = -flipr;
             }
 #undef DHTS_RING_ISSUE
         } else if (MODE == 1) {
@@ -741,10 +789,10 @@ static int sm_count_r() {
 // thread capped at 128 registers (2 CTAs of 256 threads per SM) -- forward 57 ms vs 69-89 ms for the other
 // shapes, adjoint 97 ms (every state stored) / 149 ms (K = 32) vs 106-226 ms.
 // Tuning knobs (environment), read ONCE per process: cells per thread, adjoint ring stages, forward staging.
-struct Knobs { int c_fwd, c_bwd, ring, stage, mb_fwd, xrow; };
+struct Knobs { int c_fwd, c_bwd, ring, stage, mb_fwd, xrow, mb_xfwd; };
 static const Knobs& knobs() {
     static const Knobs k = [] {
-        Knobs x{4, 4, 4, 1, 3, 1};
+        Knobs x{4, 4, 4, 1, 3, 1, 3};
         auto cells = [](const char* name, int dflt) {
             const char* e = getenv(name);
             if (!e) e = getenv("DHTS_ARZ_C");
@@ -756,6 +804,7 @@ static const Knobs& knobs() {
         if (const char* e = getenv("DHTS_ARZ_RING")) x.ring = atoi(e);      // 0 = register prefetch
         if (const char* e = getenv("DHTS_ARZ_STAGE")) x.stage = atoi(e);    // 0 = per-thread stores
         if (const char* e = getenv("DHTS_ARZ_XROW")) x.xrow = atoi(e);      // 0 = never store the interface outcomes
+        if (const char* e = getenv("DHTS_ARZ_MB_XFWD")) x.mb_xfwd = atoi(e); // forward kernel that also stores the interface outcomes
         if (const char* e = getenv("DHTS_ARZ_MB_FWD")) x.mb_fwd = atoi(e);  // 3 (default) = 80-register forward kernel, 3 CTAs per SM: 384 vs 393 ms per pass (r2c A/B); 2 = 128 registers
         return x;
     }();
@@ -781,7 +830,7 @@ template <typename T> static int plan_reg(int B, int N, bool adj, RegPlan* p, bo
     // Budget per CTA keeps two CTAs of the 128-register shape on an SM (227 KB usable, 1 KB reserved per CTA).
     p->ring_ns = 0; p->mode = 1;
     if (adj) {
-        const size_t stage = ((size_t)2 * lpc * N + (xr ? xrow_elems<T>(lpc, tpl) : 0)) * sizeof(T);
+        const size_t stage = ((size_t)2 * lpc * N + (xr ? xrow_elems<T>(lpc, tpl, C) : 0)) * sizeof(T);
         const size_t base = ring_offset<T>(lpc, p->threads / 32);
         const size_t budget = (C > 1 ? 112 : 224) * (size_t)1024;
         int ns = knobs().ring;
@@ -814,8 +863,9 @@ constexpr int NSF = 4;          // staging stages of the forward kernel
 template <typename T> static int ckpt_mode_plan(int B, int N, int K) {
     if (!knobs().xrow || K != 1 || B <= 0 || N < 1) return 0;
     RegPlan pf, pb;
-    if (plan_reg<T>(B, N, false, &pf) || pf.C <= 1 || ((size_t)N * sizeof(T)) % 16 != 0 || (N / pf.C) % 8 != 0) return 0;
-    const size_t stage = ((size_t)2 * pf.lpc * N + xrow_elems<T>(pf.lpc, N / pf.C)) * sizeof(T);
+    // whole warps per lane (the outcomes are warp ballots, stored lane by lane)
+    if (plan_reg<T>(B, N, false, &pf) || pf.C <= 1 || ((size_t)N * sizeof(T)) % 16 != 0 || (N / pf.C) % 32 != 0) return 0;
+    const size_t stage = ((size_t)2 * pf.lpc * N + xrow_elems<T>(pf.lpc, N / pf.C, pf.C)) * sizeof(T);
     if (ring_offset<T>(pf.lpc, pf.threads / 32, true) + NSF * stage > 112 * 1024) return 0;
     if (plan_reg<T>(B, N, true, &pb, true) || pb.mode != 0 || pb.C != pf.C || pb.lpc != pf.lpc) return 0;
     return 1;
@@ -829,7 +879,7 @@ template <typename T> static long long ckpt_elems(int B, int N, int steps, int K
     if (m) {
         RegPlan pf;
         plan_reg<T>(B, N, false, &pf);
-        n += ((long long)steps * B * (N / pf.C) * 2 + (long long)sizeof(T) - 1) / (long long)sizeof(T);
+        n += ((long long)steps * B * (long long)xlane_bytes(N / pf.C, pf.C) + (long long)sizeof(T) - 1) / (long long)sizeof(T);
     }
     return n;
 }
@@ -857,21 +907,21 @@ static int rollout_fwd(const T* r0, const T* y0, const T* u0, const T* ghost, co
     if (knobs().stage == 0) staged = false;
     if (xmode == 1) {   // staged, with the interface outcomes behind the states
         if (!(al16(r0) && al16(y0) && al16(u0) && al16(ckpt))) return DHTS_ERR_UNSUPPORTED;
-        const size_t smem = base + NSF * (stage + xrow_elems<T>(p.lpc, N / p.C) * sizeof(T));
+        const size_t smem = base + NSF * (stage + xrow_elems<T>(p.lpc, N / p.C, p.C) * sizeof(T));
 #define CALL(CC, MB)                                                                                                   \
     {                                                                                                                  \
         cudaFuncSetAttribute(arz_rollout_fwd_reg_kernel<T, CC, MB, NSF, false, true>,                                  \
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                                  \
         arz_rollout_fwd_reg_kernel<T, CC, MB, NSF, false, true><<<grid, p.threads, smem, st>>>(                        \
-            r0, y0, u0, ghost, nullptr, dx, umax, dt, B, N, steps, K, p.lpc, ckpt, rT, yT, uT, flags);                 \
+            r0, y0, u0, ghost, nullptr, dx, umax, dt, B, N, steps, K, p.lpc, make_rollk<T>(B, N, CC, p.lpc, p.threads / 32, true, true), ckpt, rT, yT, uT, flags); \
     }
-        // 128 registers (two CTAs per SM): at the 80 registers of three CTAs per SM the outcome bits spill (433 vs 410 ms per pass)
-        if (p.C == 8) { CALL(8, 2) } else if (p.C == 4) { CALL(4, 2) } else { CALL(2, 2) }
+        // 80 registers, three CTAs per SM by default (391 vs 405 ms per pass, r2u A/B); DHTS_ARZ_MB_XFWD=2: 128 registers
+        if (p.C == 8) { CALL(8, 2) } else if (p.C == 4) { if (knobs().mb_xfwd == 3 && smem <= 74 * 1024) { CALL(4, 3) } else { CALL(4, 2) } } else { CALL(2, 2) }
 #undef CALL
         return status_r();
     }
     if (ghost_t) {      // per-step ghosts: the variant with per-thread checkpoint stores
-#define CALL(CC, MB) arz_rollout_fwd_reg_kernel<T, CC, MB, 0, true><<<grid, p.threads, p.smem, st>>>(r0, y0, u0, nullptr, ghost_t, dx, umax, dt, B, N, steps, K, p.lpc, ckpt, rT, yT, uT, flags);
+#define CALL(CC, MB) arz_rollout_fwd_reg_kernel<T, CC, MB, 0, true><<<grid, p.threads, p.smem, st>>>(r0, y0, u0, nullptr, ghost_t, dx, umax, dt, B, N, steps, K, p.lpc, RollK(), ckpt, rT, yT, uT, flags);
         DHTS_C_DISPATCH(p, CALL)
 #undef CALL
     } else if (staged) {
@@ -881,14 +931,13 @@ static int rollout_fwd(const T* r0, const T* y0, const T* u0, const T* ghost, co
         if (smem > 48 * 1024)                                                                                          \
             cudaFuncSetAttribute(arz_rollout_fwd_reg_kernel<T, CC, MB, NSF>,                                           \
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                              \
-        arz_rollout_fwd_reg_kernel<T, CC, MB, NSF><<<grid, p.threads, smem, st>>>(r0, y0, u0, ghost, nullptr, dx, umax, dt, B,  \
-                                                                                  N, steps, K, p.lpc, ckpt, rT, yT,    \
-                                                                                  uT, flags);                          \
+        arz_rollout_fwd_reg_kernel<T, CC, MB, NSF><<<grid, p.threads, smem, st>>>(                                     \
+            r0, y0, u0, ghost, nullptr, dx, umax, dt, B, N, steps, K, p.lpc, make_rollk<T>(B, N, CC, p.lpc, p.threads / 32, true, false), ckpt, rT, yT, uT, flags); \
     }
         if (p.C == 4 && knobs().mb_fwd == 3 && base + NSF * stage <= 74 * 1024) { CALL(4, 3) } else { DHTS_C_DISPATCH(p, CALL) }
 #undef CALL
     } else {
-#define CALL(CC, MB) arz_rollout_fwd_reg_kernel<T, CC, MB, 0><<<grid, p.threads, p.smem, st>>>(r0, y0, u0, ghost, nullptr, dx, umax, dt, B, N, steps, K, p.lpc, ckpt, rT, yT, uT, flags);
+#define CALL(CC, MB) arz_rollout_fwd_reg_kernel<T, CC, MB, 0><<<grid, p.threads, p.smem, st>>>(r0, y0, u0, ghost, nullptr, dx, umax, dt, B, N, steps, K, p.lpc, RollK(), ckpt, rT, yT, uT, flags);
         DHTS_C_DISPATCH(p, CALL)
 #undef CALL
     }
@@ -957,7 +1006,7 @@ static int rollout_bwd(const T* ckpt, const T* u0, const T* ghost, const T* ghos
         grid = (int)(g < p.grid ? g : p.grid);                                                                         \
         arz_rollout_bwd_reg_kernel<T, CC, MB, 0, false, true><<<grid, p.threads, p.smem, st>>>(                           \
             ckpt, u0, ghost, nullptr, nullptr, nullptr, dx, umax, dt, B, N, steps, K, p.lpc, rT, yT, g_rT, g_yT, g_uT, \
-            scratch, g_r0, g_y0, g_ghost, flags, p.ring_ns);                                                           \
+            scratch, g_r0, g_y0, g_ghost, flags, p.ring_ns, make_rollk<T>(B, N, CC, p.lpc, p.threads / 32, false, true)); \
     }
         if (p.C == 8) { CALL(8, 2) } else if (p.C == 4) { CALL(4, 2) } else { CALL(2, 2) }
 #undef CALL
@@ -975,7 +1024,7 @@ static int rollout_bwd(const T* ckpt, const T* u0, const T* ghost, const T* ghos
 #define CALL(CC, MB)                                                                                                   \
     arz_rollout_bwd_reg_kernel<T, CC, MB, 1, true><<<grid, p.threads, p.smem, st>>>(                                   \
         ckpt, u0, ghost_t ? nullptr : ghost, ghost_t, g_hist, g_ghost_t, dx, umax, dt, B, N, steps, K, p.lpc, rT, yT,  \
-        g_rT, g_yT, g_uT, scratch, g_r0, g_y0, g_ghost, flags, 0);
+        g_rT, g_yT, g_uT, scratch, g_r0, g_y0, g_ghost, flags, 0, RollK());
         DHTS_C_DISPATCH(p, CALL)
 #undef CALL
         return status_r();
@@ -987,7 +1036,7 @@ static int rollout_bwd(const T* ckpt, const T* u0, const T* ghost, const T* ghos
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);                            \
         arz_rollout_bwd_reg_kernel<T, CC, MB, MD><<<grid, p.threads, p.smem, st>>>(                                    \
             ckpt, u0, ghost, nullptr, nullptr, nullptr, dx, umax, dt, B, N, steps, K, p.lpc, rT, yT, g_rT, g_yT, g_uT, \
-            scratch, g_r0, g_y0, g_ghost, flags, p.ring_ns);                                                           \
+            scratch, g_r0, g_y0, g_ghost, flags, p.ring_ns, make_rollk<T>(B, N, CC, p.lpc, p.threads / 32, false, false)); \
     }
     DHTS_CM_DISPATCH(p)
 #undef CALLM

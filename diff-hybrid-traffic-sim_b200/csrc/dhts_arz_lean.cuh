@@ -164,12 +164,12 @@ __device__ __forceinline__ void fflux(const FRec<T>& L, T Rr, T Rus, const LaneK
     fy = t.isL ? L.fy : y0 * u0;
 }
 
-// Stored interface outcome (forward -> adjoint through HBM): two bits per interface and step (bit 0: Q_L, bit 1: Q_M).  With
-// them the adjoint skips the case tree.  (Storing sqrt(r0 + eps) of the selected state as well -- 8 bytes per cell-step, so
-// that the adjoint skips that square root too -- was measured: adjoint 629 -> 580 ms per pass but forward 381 -> 411 ms, the
-// forward kernel does not take 24 instead of 16 bytes of writes per cell-step for free.)
+// Stored interface outcome (forward -> adjoint through HBM): two bits per interface and step (Q_L, Q_M).  With them the
+// adjoint skips the case tree.  (Storing sqrt(r0 + eps) of the selected state as well -- 8 bytes per cell-step, so that the
+// adjoint skips that square root too -- was measured: adjoint 629 -> 580 ms per pass but forward 381 -> 411 ms, the forward
+// kernel does not take 24 instead of 16 bytes of writes per cell-step for free.)
 template <typename T, bool VAC = true>
-__device__ __forceinline__ void fflux_x(const FRec<T>& L, T Rr, T Rus, const LaneK<T>& k, T& fr, T& fy, unsigned& bits) {
+__device__ __forceinline__ void fflux_x(const FRec<T>& L, T Rr, T Rus, const LaneK<T>& k, T& fr, T& fy, bool& isL, bool& isM) {
     const Tree<T> t = case_tree<T, VAC>(L.r, L.us, L.sq, L.w, Rr, Rus, k);
     const T root = t.isM ? t.b : t.q;
     const T r0 = root * root;
@@ -178,7 +178,7 @@ __device__ __forceinline__ void fflux_x(const FRec<T>& L, T Rr, T Rus, const Lan
     const T y0 = r0 * (u0 - ueq);
     fr = t.isL ? L.fr : r0 * u0;
     fy = t.isL ? L.fy : y0 * u0;
-    bits = (t.isL ? 1u : 0u) | (t.isM ? 2u : 0u);
+    isL = t.isL; isM = t.isM;
 }
 
 // ---------------------------------------------------------------------------- adjoint
@@ -268,9 +268,8 @@ __device__ __forceinline__ void aflux(const ARec<T>& L, const ARec<T>& R, T wr, 
 // aflux with the interface's outcome stored by the forward pass (fflux_x): no case tree.
 // Uses us, sq, f00, f10, f11, plr, ri of L and us, plr, ri, ueqp of R.
 template <typename T>
-__device__ __forceinline__ void aflux_x(const ARec<T>& L, const ARec<T>& R, T wr, T wy, const LaneK<T>& k, unsigned bits, T& par,
-                                        T& pay, T& pbr, T& pby) {
-    const bool isL = bits & 1u, isM = bits & 2u;
+__device__ __forceinline__ void aflux_x(const ARec<T>& L, const ARec<T>& R, T wr, T wy, const LaneK<T>& k, bool isL, bool isM,
+                                        T& par, T& pay, T& pbr, T& pby) {
     const T b = fma(L.us - R.us, k.inv_umax, L.sq);                // Q_M: r_m = b^2
     const T sc = fma(k.umax, L.sq, L.us);                          // Q_C: r_c = q^2, u_c = sc / 3
     const T root = isM ? b : sc * k.inv15;
