@@ -329,9 +329,9 @@ __device__ __forceinline__ bool chunk_fwd_step(T* r, T* y, const T* us, bool fir
 // NS > 0 (every state stored, K == 1): the state rows go to HBM through an NS-stage shared-memory staging ring and
 // TMA bulk stores issued by one thread -- no per-thread STG, no store address arithmetic, and the state registers
 // are free again as soon as the STS has read them.  NS == 0: per-thread vector stores (sparse checkpoints).
-// XR (staged mode only): besides (r, y) every state stores the OUTCOME of each interface of the step taken from it -- one
-// halfword per thread, behind the states in `ckpt` -- which lets the adjoint skip the case tree (aflux_x) for half a byte
-// per cell-step of HBM traffic.
+// XR (staged mode only): besides (r, y) every state stores the OUTCOME of each interface of the step taken from it -- warp
+// ballots, behind the states in `ckpt` -- which lets the adjoint skip the case tree (aflux_x) for a quarter byte per
+// cell-step of HBM traffic.
 // Outcome rows: C ballot pairs (8 bytes each) per warp and step, i.e. tpl / 32 * C * 8 = N / 4 bytes per lane and step.
 __host__ __device__ inline size_t xlane_bytes(int tpl, int C) { return (size_t)(tpl / 32) * C * 8; }
 template <typename T> __host__ __device__ inline size_t xrow_elems(int lpc, int tpl, int C) {      // outcome row of a stage, in elements

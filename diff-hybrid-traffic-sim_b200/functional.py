@@ -94,8 +94,8 @@ def idm_rollout_state(p0, v0, params, lane_off, head, dt, steps, ckpt_every, fla
 
 def arz_ckpt_elems(B, N, steps, ckpt_every, dtype) -> int:
     """Elements a caller-owned ``ckpt_buffer`` must hold for a differentiable rollout of this shape: the stored states
-    [ceil(steps / ckpt_every), 2, B, N] plus, where the kernels store them, the interface outcomes of every step (half a byte
-    per cell-step; ``dhts_arz_rollout_ckpt_elems_*``, include/dhts.h)."""
+    [ceil(steps / ckpt_every), 2, B, N] plus, where the kernels store them, the interface outcomes of every step (a quarter
+    byte per cell-step; ``dhts_arz_rollout_ckpt_elems_*``, include/dhts.h)."""
     return _arz_ckpt_elems(B, N, steps, ckpt_every, dtype)[0]
 
 

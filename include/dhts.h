@@ -102,9 +102,10 @@ int dhts_arz_step_bwd_f32(const float* r_pad, const float* y_pad, const float* u
  *   ckpt [S][2][B][N] (+ outcomes) or NULL, S = ceil(steps/ckpt_every): state BEFORE steps
  *                          0, K, 2K, ... (needed by the backward entry point)
  *   ckpt_mode              0: ckpt holds the states only.  1: behind the S states it also holds the OUTCOME of every
- *                          interface of every step (Q_L / Q_M / Q_C, _arz.py:324-336: two bits per interface, one
- *                          halfword per thread and step), which lets the adjoint skip the Riemann case tree for half a
- *                          byte per cell-step of HBM traffic.  dhts_arz_rollout_ckpt_elems_*(B, N, steps, ckpt_every,
+ *                          interface of every step (Q_L / Q_M / Q_C, _arz.py:324-336: two bits per interface, kept as
+ *                          the warp ballots of the kernels' thread -> cell mapping, N / 4 bytes per lane and step),
+ *                          which lets the adjoint skip the Riemann case tree for a quarter byte per cell-step of HBM
+ *                          traffic.  dhts_arz_rollout_ckpt_elems_*(B, N, steps, ckpt_every,
  *                          &mode) returns the elements `ckpt` must hold and the mode the kernels take for this shape
  *                          (1 where every state is stored, the ghosts are static and the staged forward / ring adjoint
  *                          kernels apply); callers pass that mode to both calls (0 is always accepted)
