@@ -31,6 +31,24 @@ template <> __device__ __forceinline__ float t_sqrt<float>(float x) { return sqr
 __device__ __forceinline__ double t_abs(double x) { return fabs(x); }
 __device__ __forceinline__ float t_abs(float x) { return fabsf(x); }
 
+// fp64 constants that are not 32-bit immediates live in constant memory: an FP64 instruction takes a constant-bank operand for
+// free, whereas a literal costs two moves into a register pair every time the compiler rematerialises it (it does, under the
+// rollouts' register caps: ~20 of the adjoint's ~630 instructions per warp-step were such moves).
+static __constant__ double dhts_kd[4] = {1e-5, 316.22776601683796 /* 1/sqrt(1e-5) */, 0.375, 0.5 / 1.5};
+template <typename T> struct KC;
+template <> struct KC<double> {
+    static __device__ __forceinline__ double eps() { return dhts_kd[0]; }
+    static __device__ __forceinline__ double rsqrt_eps() { return dhts_kd[1]; }
+    static __device__ __forceinline__ double c375() { return dhts_kd[2]; }
+    static __device__ __forceinline__ double third() { return dhts_kd[3]; }
+};
+template <> struct KC<float> {
+    static __device__ __forceinline__ float eps() { return 1e-5f; }
+    static __device__ __forceinline__ float rsqrt_eps() { return 316.22776601683796f; }
+    static __device__ __forceinline__ float c375() { return 0.375f; }
+    static __device__ __forceinline__ float third() { return 0.5f / 1.5f; }
+};
+
 // Branch-free 1/sqrt(x) and 1/x for well-scaled positive x (densities, gaps): hardware
 // approximation (MUFU.RSQ64H / MUFU.RCP64H, ~2^-22) refined by one cubic step to ~1 ulp.  The library
 // sqrt()/division carry special-case slow paths and long dependent Newton chains that
@@ -40,9 +58,17 @@ template <> __device__ __forceinline__ double f_rsqrt<double>(double x) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     double e = fma(-(x * y), y, 1.0);                 // 1 - x y^2
-    return fma(y, e * fma(0.375, e, 0.5), y);         // Halley step: error^3 -> below 1 ulp
+    return fma(y, e * fma(dhts_kd[2], e, 0.5), y);         // Halley step: error^3 -> below 1 ulp
 }
 template <> __device__ __forceinline__ float f_rsqrt<float>(float x) { return rsqrtf(x); }
+// the same with the 0.375 as a literal (adjoint kernels: there the compiler does better with literals, see KC)
+template <typename T> __device__ __forceinline__ T f_rsqrt_lit(T x) { return f_rsqrt<T>(x); }
+template <> __device__ __forceinline__ double f_rsqrt_lit<double>(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-(x * y), y, 1.0);
+    return fma(y, e * fma(0.375, e, 0.5), y);
+}
 template <typename T> __device__ __forceinline__ T f_rcp(T x);
 template <> __device__ __forceinline__ double f_rcp<double>(double x) {
     double y;
@@ -71,8 +97,10 @@ template <> __device__ __forceinline__ float f_sqrt_pos<float>(float x) {
 template <typename T> __device__ __forceinline__ T t_max(T a, T b) { return a > b ? a : b; }
 template <typename T> __device__ __forceinline__ bool t_isnan(T x) { return !(x == x); }
 
-#define DHTS_EPS (T(1e-5))
-#define DHTS_RSQRT_EPS (T(316.22776601683796))   // 1/sqrt(1e-5)
+#define DHTS_EPS (KC<T>::eps())
+#define DHTS_RSQRT_EPS (KC<T>::rsqrt_eps())   // 1/sqrt(1e-5)
+#define DHTS_EPS_LIT (T(1e-5))
+#define DHTS_RSQRT_EPS_LIT (T(316.22776601683796))
 
 // Per-cell record.  The reference STORES u and u_eq on each cell instead of
 // recomputing them at use:

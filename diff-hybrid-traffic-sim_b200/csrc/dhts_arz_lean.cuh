@@ -157,7 +157,7 @@ __device__ __forceinline__ void fflux(const FRec<T>& L, T Rr, T Rus, const LaneK
     const Tree<T> t = case_tree<T, VAC>(L.r, L.us, L.sq, L.w, Rr, Rus, k);
     const T root = t.isM ? t.b : t.q;
     const T r0 = root * root;
-    const T u0 = t.isM ? Rus : t.sc * (T(0.5) / T(1.5));
+    const T u0 = t.isM ? Rus : t.sc * KC<T>::third();
     const T ueq = fma(-k.umax, f_sqrt_pos(fma(root, root, DHTS_EPS)), k.umax);
     const T y0 = r0 * (u0 - ueq);
     fr = t.isL ? L.fr : r0 * u0;
@@ -173,7 +173,7 @@ __device__ __forceinline__ void fflux_x(const FRec<T>& L, T Rr, T Rus, const Lan
     const Tree<T> t = case_tree<T, VAC>(L.r, L.us, L.sq, L.w, Rr, Rus, k);
     const T root = t.isM ? t.b : t.q;
     const T r0 = root * root;
-    const T u0 = t.isM ? Rus : t.sc * (T(0.5) / T(1.5));
+    const T u0 = t.isM ? Rus : t.sc * KC<T>::third();
     const T ueq = fma(-k.umax, f_sqrt_pos(fma(root, root, DHTS_EPS)), k.umax);
     const T y0 = r0 * (u0 - ueq);
     fr = t.isL ? L.fr : r0 * u0;
@@ -200,10 +200,10 @@ template <typename T> __device__ __forceinline__ ARec<T> unpack_a(const T* a) {
 template <typename T, bool STORED, bool VAC = true>
 __device__ __forceinline__ ARec<T> aderive(T r, T y, T us_in, const LaneK<T>& k) {
     ARec<T> c;
-    const T rc = VAC ? t_max(r, DHTS_EPS) : r;
-    const T rs = f_rsqrt(rc);
+    const T rc = VAC ? t_max(r, DHTS_EPS_LIT) : r;
+    const T rs = f_rsqrt_lit(rc);
     const T ri = rs * rs;
-    const T se = f_sqrt_pos(rc + DHTS_EPS);
+    const T se = f_sqrt_pos(rc + DHTS_EPS_LIT);
     const T uf = fma(-k.umax, se, k.umax);
     const T yri = y * ri;
     c.r = r; c.sq = rc * rs; c.ri = ri;
@@ -218,10 +218,10 @@ __device__ __forceinline__ ARec<T> aderive(T r, T y, T us_in, const LaneK<T>& k)
 }
 // r < eps: the fresh u_eq(r) enters w, f00 and f11 (the clamped one stays in us)
 template <typename T> __device__ __forceinline__ void fix_vacuum_adj(ARec<T>& c, T y, const LaneK<T>& k) {
-    const T om = T(1) - f_sqrt_pos(t_max(c.r, T(0)) + DHTS_EPS);
+    const T om = T(1) - f_sqrt_pos(t_max(c.r, T(0)) + DHTS_EPS_LIT);
     const T uf = k.umax * om;
     c.w = fma(-k.umax, om, k.umax + c.us);              // bitwise w_vacuum
-    c.f00 = fma(DHTS_EPS, c.ueqp, uf);
+    c.f00 = fma(DHTS_EPS_LIT, c.ueqp, uf);
     c.f11 = fma(T(2), y * c.ri, uf);
 }
 
@@ -234,13 +234,13 @@ __device__ __forceinline__ void aflux(const ARec<T>& L, const ARec<T>& R, T wr, 
     const T r0 = root * root;
     const T rootr = t_abs(root);
     const T u0 = t.isM ? R.us : t.sc * (T(0.5) / T(1.5));
-    const T ueq0 = fma(-k.umax, f_sqrt_pos(fma(root, root, DHTS_EPS)), k.umax);
+    const T ueq0 = fma(-k.umax, f_sqrt_pos(fma(root, root, DHTS_EPS_LIT)), k.umax);
     const T g = u0 - ueq0;
     const T y0 = r0 * g;
     // flux_prime at Q0 with r clamped at eps
-    const bool big = r0 >= DHTS_EPS;
-    const T inv_sq = big ? f_rcp(rootr) : DHTS_RSQRT_EPS;      // rootr >= sqrt(eps) where it is selected; a non-finite value in the other arm is discarded
-    const T rr = big ? r0 : DHTS_EPS;
+    const bool big = r0 >= DHTS_EPS_LIT;
+    const T inv_sq = big ? f_rcp(rootr) : DHTS_RSQRT_EPS_LIT;      // rootr >= sqrt(eps) where it is selected; a non-finite value in the other arm is discarded
+    const T rr = big ? r0 : DHTS_EPS_LIT;
     const T ueqp0 = -k.hum * inv_sq;
     const T yr = y0 * (inv_sq * inv_sq);
     const T f00 = fma(rr, ueqp0, ueq0);
@@ -276,12 +276,12 @@ __device__ __forceinline__ void aflux_x(const ARec<T>& L, const ARec<T>& R, T wr
     const T r0 = root * root;
     const T rootr = t_abs(root);
     const T u0 = isM ? R.us : sc * (T(0.5) / T(1.5));
-    const T ueq0 = fma(-k.umax, f_sqrt_pos(fma(root, root, DHTS_EPS)), k.umax);
+    const T ueq0 = fma(-k.umax, f_sqrt_pos(fma(root, root, DHTS_EPS_LIT)), k.umax);
     const T g = u0 - ueq0;
     const T y0 = r0 * g;
-    const bool big = r0 >= DHTS_EPS;
-    const T inv_sq = big ? f_rcp(rootr) : DHTS_RSQRT_EPS;
-    const T rr = big ? r0 : DHTS_EPS;
+    const bool big = r0 >= DHTS_EPS_LIT;
+    const T inv_sq = big ? f_rcp(rootr) : DHTS_RSQRT_EPS_LIT;
+    const T rr = big ? r0 : DHTS_EPS_LIT;
     const T ueqp0 = -k.hum * inv_sq;
     const T yr = y0 * (inv_sq * inv_sq);
     const T f00 = fma(rr, ueqp0, ueq0);

@@ -150,6 +150,41 @@ def test_rollout_vs_oracle_shapes(dev, B, N, T, K):
     assert relerr(torch.stack([tgr.grad, tgu.grad], -1).cpu(), o["g_ghost"]) < 1e-8
 
 
+@pytest.mark.parametrize("B,N,T,K", [(6, 1024, 40, 1), (6, 1024, 40, 8), (37, 64, 30, 1), (9, 128, 25, 1), (4, 100, 30, 5)])
+def test_rollout_with_vacuum_vs_oracle(dev, B, N, T, K):
+    """Lanes with EMPTY stretches (r = 0), near-vacuum cells on both sides of eps = 1e-5 and vacuum ghosts: the warp-voted
+    vacuum variants of the forward / adjoint sweeps (fix-ups of w, f00, f11; clamps at eps), on the staged + stored-outcome
+    path (ckpt_every = 1: the adjoint picks its variant from its own cells, the outcomes come from the forward pass), the
+    recompute path and the many-lanes-per-CTA shapes.  _arz.py:225-322 (vacuum branches of the case tree), darz.py:217-233."""
+    import dhts_b200
+    from dhts_b200 import functional as F
+    from oracle import oracle as O
+    rng = np.random.default_rng(7 * B + N + K)
+    dx = rng.uniform(4.0, 6.0, B); umax = rng.uniform(25.0, 35.0, B); dt = 0.01
+    r0 = rng.uniform(0, 1, (B, N)); u0 = rng.uniform(0, 1, (B, N)) * umax[:, None]
+    for b in range(B):
+        for _ in range(3):      # empty stretches and near-vacuum stretches (some cells just below, some just above eps)
+            a = int(rng.integers(0, N - 8)); w = int(rng.integers(3, max(4, N // 6)))
+            r0[b, a:a + w] = 0.0
+            a = int(rng.integers(0, N - 8)); w = int(rng.integers(3, max(4, N // 8)))
+            r0[b, a:a + w] = 10.0 ** rng.uniform(-7, -4, size=r0[b, a:a + w].shape)
+    gh = np.stack([rng.uniform(0, 1, (B, 2)), rng.uniform(0, 1, (B, 2)) * umax[:, None]], -1)
+    gh[::2, 0, 0] = 0.0; gh[1::3, 1, 0] = 3e-6                  # vacuum ghosts
+    wr = rng.normal(size=(B, N)); wu = rng.normal(size=(B, N)) / 30
+    flags = dhts_b200.Flags(dev)
+    tr = T64(r0, dev).requires_grad_(); tu = T64(u0, dev).requires_grad_()
+    tgr = T64(gh[:, :, 0], dev).requires_grad_(); tgu = T64(gh[:, :, 1], dev).requires_grad_()
+    rT, yT, uT = F.arz_rollout(tr, tu, tgr, tgu, T64(dx, dev), T64(umax, dev), dt, T, ckpt_every=K, flags=flags)
+    ((rT * T64(wr, dev)).sum() + (uT * T64(wu, dev)).sum()).backward()
+    flags.check()
+    o = O.arz_rollout(r0, u0, gh, dx, umax, dt, T, g_rT=wr, g_uT=wu)
+    assert o["cfl"] == 0
+    assert (o["rT"] < 1e-5).any()                                # vacuum cells survive to the end of the rollout
+    assert relerr(rT.detach().cpu(), o["rT"]) < 1e-9 and relerr(uT.detach().cpu(), o["uT"]) < 1e-9
+    assert relerr(tr.grad.cpu(), o["g_r0"]) < 1e-8 and relerr(tu.grad.cpu(), o["g_u0"]) < 1e-8
+    assert relerr(torch.stack([tgr.grad, tgu.grad], -1).cpu(), o["g_ghost"]) < 1e-8
+
+
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
 def test_rollout_tma_paths_equal_plain_paths(dev, dtype):
     """Every state stored: the forward's staged TMA bulk stores (shared-memory staging ring, cp.async.bulk to HBM) and
