@@ -201,14 +201,16 @@ template <typename T> __device__ __forceinline__ Shm<T> carve_shm(unsigned char*
     return s;
 }
 
+// dx == null: every lane has the geometry `kall` (computed on the host; dx and umax are given together or not at all).
 template <typename T>
 __device__ __forceinline__ void setup_group(const Shm<T>& s, int lane0, int nl, const T* __restrict__ ghost,
-                                            const T* __restrict__ dx, const T* __restrict__ umax_, T dt, bool fwd = false) {
-    for (int l = threadIdx.x; l < nl; l += blockDim.x) s.lk[l] = make_lanek<T>(umax_[lane0 + l], dx[lane0 + l], dt);
+                                            const T* __restrict__ dx, const T* __restrict__ umax_, const LaneK<T>& kall, T dt,
+                                            bool fwd = false) {
+    for (int l = threadIdx.x; l < nl; l += blockDim.x) s.lk[l] = dx ? make_lanek<T>(umax_[lane0 + l], dx[lane0 + l], dt) : kall;
     for (int e = threadIdx.x; e < nl * 2 && ghost; e += blockDim.x) {      // ghost == null: per-step ghosts (step_ghost_record)
         int l = e >> 1, side = e & 1;
         const T* g = ghost + ((size_t)(lane0 + l) * 2 + side) * 3;          // (r, y, u) built by from_r_u
-        const LaneK<T> k = make_lanek<T>(umax_[lane0 + l], dx[lane0 + l], dt);
+        const LaneK<T> k = dx ? make_lanek<T>(umax_[lane0 + l], dx[lane0 + l], dt) : kall;
         FRec<T> f = fderive<T, true>(g[0], g[1], g[2], k);
         if (g[0] < DHTS_EPS) f.w = w_vacuum(g[0], f.us, k);
         pack(f, s.ghostF + (l * 2 + side) * GH_F);
@@ -357,11 +359,13 @@ template <typename T> static RollK make_rollk(int B, int N, int C, int lpc, int 
     return k;
 }
 
-template <typename T, int C, int MB, int NS, bool TV = false, bool XR = false>
+// UNI: all lanes share one geometry (dx == umax_ == null) and the kernel reads the lane constants from its PARAMETERS (`kall`,
+// constant bank: free operands of the fp64 instructions) instead of keeping them in 12-14 registers per thread.
+template <typename T, int C, int MB, int NS, bool TV = false, bool XR = false, bool UNI = false>
 __global__ void __launch_bounds__(1024 / (C < 4 ? C : 4), MB) arz_rollout_fwd_reg_kernel(const T* __restrict__ r0, const T* __restrict__ y0,
                                            const T* __restrict__ u0, const T* __restrict__ ghost,
                                            const T* __restrict__ ghost_t,
-                                           const T* __restrict__ dx, const T* __restrict__ umax_, T dt, int B, int N,
+                                           const T* __restrict__ dx, const T* __restrict__ umax_, const LaneK<T> kall, T dt, int B, int N,
                                            int steps, int K, int lpc, const RollK rk, T* __restrict__ ckpt, T* __restrict__ rT,
                                            T* __restrict__ yT, T* __restrict__ uT, int* __restrict__ flags) {
     extern __shared__ __align__(128) unsigned char raw[];
@@ -378,9 +382,9 @@ __global__ void __launch_bounds__(1024 / (C < 4 ? C : 4), MB) arz_rollout_fwd_re
         const bool active = l < nl;
         const int ll = active ? l : 0;
         __syncthreads();
-        setup_group(s, lane0, nl, ghost, dx, umax_, dt, true);
+        setup_group(s, lane0, nl, ghost, dx, umax_, kall, dt, true);
         __syncthreads();
-        const LaneK<T> k = s.lk[ll];
+        const LaneK<T> k = UNI ? kall : s.lk[ll];
         const T* gL = s.ghostF + (ll * 2) * GH_F; const T* gR = gL + GH_F;
         const size_t off = (size_t)(lane0 + ll) * N + (size_t)kc * C;
         const size_t soff = (size_t)ll * N + (size_t)kc * C;
@@ -553,12 +557,12 @@ __device__ __forceinline__ bool chunk_adj_step(const T* r, const T* y, const T* 
 // EXT (MODE 1 only): per-step ghosts ghost_t [steps][B][2][3] with their adjoints g_ghost_t [steps][B][2][2], and g_hist
 // [steps][2][B][N], the adjoint of a loss that reads the state BEFORE every step (added once that step's VJP has run).
 // XR (MODE 0 only): the forward pass stored the interface outcomes behind the states (see the forward kernel).
-template <typename T, int C, int MB, int MODE, bool EXT = false, bool XR = false>
+template <typename T, int C, int MB, int MODE, bool EXT = false, bool XR = false, bool UNI = false>
 __global__ void __launch_bounds__(1024 / (C < 4 ? C : 4), MB) arz_rollout_bwd_reg_kernel(const T* __restrict__ ckpt, const T* __restrict__ u0,
                                            const T* __restrict__ ghost, const T* __restrict__ ghost_t,
                                            const T* __restrict__ g_hist, T* __restrict__ g_ghost_t,
                                            const T* __restrict__ dx,
-                                           const T* __restrict__ umax_, T dt, int B, int N, int steps, int K, int lpc,
+                                           const T* __restrict__ umax_, const LaneK<T> kall, T dt, int B, int N, int steps, int K, int lpc,
                                            const T* __restrict__ rT, const T* __restrict__ yT,
                                            const T* __restrict__ g_rT, const T* __restrict__ g_yT,
                                            const T* __restrict__ g_uT, T* __restrict__ scratch,
@@ -595,9 +599,9 @@ __global__ void __launch_bounds__(1024 / (C < 4 ? C : 4), MB) arz_rollout_bwd_re
         const int ll = active ? l : 0;
         const bool first_chunk = kc == 0, last_chunk = kc == tpl - 1;
         __syncthreads();
-        setup_group(s, lane0, nl, ghost, dx, umax_, dt);
+        setup_group(s, lane0, nl, ghost, dx, umax_, kall, dt);
         __syncthreads();
-        const LaneK<T> k = s.lk[ll];
+        const LaneK<T> k = UNI ? kall : s.lk[ll];
         const T* gLf = s.ghostF + (ll * 2) * GH_F; const T* gRf = gLf + GH_F;
         const T* gLa = s.ghostA + (ll * 2) * GH_A; const T* gRa = gLa + GH_A;
         const size_t off = (size_t)(lane0 + ll) * N + (size_t)kc * C;
@@ -789,10 +793,10 @@ static int sm_count_r() {
 // thread capped at 128 registers (2 CTAs of 256 threads per SM) -- forward 57 ms vs 69-89 ms for the other
 // shapes, adjoint 97 ms (every state stored) / 149 ms (K = 32) vs 106-226 ms.
 // Tuning knobs (environment), read ONCE per process: cells per thread, adjoint ring stages, forward staging.
-struct Knobs { int c_fwd, c_bwd, ring, stage, mb_fwd, xrow, mb_xfwd; };
+struct Knobs { int c_fwd, c_bwd, ring, stage, mb_fwd, xrow, mb_xfwd, uni; };
 static const Knobs& knobs() {
     static const Knobs k = [] {
-        Knobs x{4, 4, 4, 1, 3, 1, 3};
+        Knobs x{4, 4, 4, 1, 3, 1, 3, 1};
         auto cells = [](const char* name, int dflt) {
             const char* e = getenv(name);
             if (!e) e = getenv("DHTS_ARZ_C");
@@ -804,6 +808,7 @@ static const Knobs& knobs() {
         if (const char* e = getenv("DHTS_ARZ_RING")) x.ring = atoi(e);      // 0 = register prefetch
         if (const char* e = getenv("DHTS_ARZ_STAGE")) x.stage = atoi(e);    // 0 = per-thread stores
         if (const char* e = getenv("DHTS_ARZ_XROW")) x.xrow = atoi(e);      // 0 = never store the interface outcomes
+        if (const char* e = getenv("DHTS_ARZ_UNI")) x.uni = atoi(e);         // 0: uniform-geometry calls run the per-lane-constant kernels
         if (const char* e = getenv("DHTS_ARZ_MB_XFWD")) x.mb_xfwd = atoi(e); // forward kernel that also stores the interface outcomes
         if (const char* e = getenv("DHTS_ARZ_MB_FWD")) x.mb_fwd = atoi(e);  // 3 (default) = 80-register forward kernel, 3 CTAs per SM: 384 vs 393 ms per pass (r2c A/B); 2 = 128 registers
         return x;
@@ -886,9 +891,13 @@ template <typename T> static long long ckpt_elems(int B, int N, int steps, int K
 
 template <typename T>
 static int rollout_fwd(const T* r0, const T* y0, const T* u0, const T* ghost, const T* ghost_t, const T* dx, const T* umax,
-                       T dt, int B, int N, int steps, int K, int xmode, T* ckpt, T* rT, T* yT, T* uT, int* flags, cudaStream_t st) {
-    if (!r0 || !y0 || (!ghost && !ghost_t) || !dx || !umax || !rT || !yT || !uT || !flags || B < 0 || N < 1 || steps < 0)
+                       T dx_all, T umax_all, T dt, int B, int N, int steps, int K, int xmode, T* ckpt, T* rT, T* yT, T* uT,
+                       int* flags, cudaStream_t st) {
+    if (!r0 || !y0 || (!ghost && !ghost_t) || (!dx != !umax) || !rT || !yT || !uT || !flags || B < 0 || N < 1 || steps < 0)
         return DHTS_ERR_INVALID;
+    const bool uni = !dx;                         // one geometry for all lanes: the lane constants travel as a kernel parameter
+    if (uni && !(dx_all > T(0) && umax_all > T(0))) return DHTS_ERR_INVALID;
+    const LaneK<T> kall = make_lanek<T>(uni ? umax_all : T(1), uni ? dx_all : T(1), dt);
     if (ckpt && K < 1) return DHTS_ERR_INVALID;
     if (xmode != 0 && xmode != 1) return DHTS_ERR_INVALID;
     if (xmode == 1 && (!ckpt || ghost_t || ckpt_mode_plan<T>(B, N, K) != 1)) return DHTS_ERR_INVALID;
@@ -913,15 +922,26 @@ static int rollout_fwd(const T* r0, const T* y0, const T* u0, const T* ghost, co
         cudaFuncSetAttribute(arz_rollout_fwd_reg_kernel<T, CC, MB, NSF, false, true>,                                  \
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                                  \
         arz_rollout_fwd_reg_kernel<T, CC, MB, NSF, false, true><<<grid, p.threads, smem, st>>>(                        \
-            r0, y0, u0, ghost, nullptr, dx, umax, dt, B, N, steps, K, p.lpc, make_rollk<T>(B, N, CC, p.lpc, p.threads / 32, true, true), ckpt, rT, yT, uT, flags); \
+            r0, y0, u0, ghost, nullptr, dx, umax, kall, dt, B, N, steps, K, p.lpc, make_rollk<T>(B, N, CC, p.lpc, p.threads / 32, true, true), ckpt, rT, yT, uT, flags); \
     }
         // 80 registers, three CTAs per SM by default (391 vs 405 ms per pass, r2u A/B); DHTS_ARZ_MB_XFWD=2: 128 registers
-        if (p.C == 8) { CALL(8, 2) } else if (p.C == 4) { if (knobs().mb_xfwd == 3 && smem <= 74 * 1024) { CALL(4, 3) } else { CALL(4, 2) } } else { CALL(2, 2) }
+#define CALLU(CC, MB)                                                                                                  \
+    {                                                                                                                  \
+        cudaFuncSetAttribute(arz_rollout_fwd_reg_kernel<T, CC, MB, NSF, false, true, true>,                            \
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                                  \
+        arz_rollout_fwd_reg_kernel<T, CC, MB, NSF, false, true, true><<<grid, p.threads, smem, st>>>(                  \
+            r0, y0, u0, ghost, nullptr, dx, umax, kall, dt, B, N, steps, K, p.lpc, make_rollk<T>(B, N, CC, p.lpc, p.threads / 32, true, true), ckpt, rT, yT, uT, flags); \
+    }
+        const bool mb3 = knobs().mb_xfwd == 3 && smem <= 74 * 1024;
+        if (p.C == 8) { CALL(8, 2) }
+        else if (p.C == 4) { if (uni && knobs().uni) { if (mb3) { CALLU(4, 3) } else { CALLU(4, 2) } } else if (mb3) { CALL(4, 3) } else { CALL(4, 2) } }
+        else { CALL(2, 2) }
 #undef CALL
+#undef CALLU
         return status_r();
     }
     if (ghost_t) {      // per-step ghosts: the variant with per-thread checkpoint stores
-#define CALL(CC, MB) arz_rollout_fwd_reg_kernel<T, CC, MB, 0, true><<<grid, p.threads, p.smem, st>>>(r0, y0, u0, nullptr, ghost_t, dx, umax, dt, B, N, steps, K, p.lpc, RollK(), ckpt, rT, yT, uT, flags);
+#define CALL(CC, MB) arz_rollout_fwd_reg_kernel<T, CC, MB, 0, true><<<grid, p.threads, p.smem, st>>>(r0, y0, u0, nullptr, ghost_t, dx, umax, kall, dt, B, N, steps, K, p.lpc, RollK(), ckpt, rT, yT, uT, flags);
         DHTS_C_DISPATCH(p, CALL)
 #undef CALL
     } else if (staged) {
@@ -932,12 +952,12 @@ static int rollout_fwd(const T* r0, const T* y0, const T* u0, const T* ghost, co
             cudaFuncSetAttribute(arz_rollout_fwd_reg_kernel<T, CC, MB, NSF>,                                           \
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                              \
         arz_rollout_fwd_reg_kernel<T, CC, MB, NSF><<<grid, p.threads, smem, st>>>(                                     \
-            r0, y0, u0, ghost, nullptr, dx, umax, dt, B, N, steps, K, p.lpc, make_rollk<T>(B, N, CC, p.lpc, p.threads / 32, true, false), ckpt, rT, yT, uT, flags); \
+            r0, y0, u0, ghost, nullptr, dx, umax, kall, dt, B, N, steps, K, p.lpc, make_rollk<T>(B, N, CC, p.lpc, p.threads / 32, true, false), ckpt, rT, yT, uT, flags); \
     }
         if (p.C == 4 && knobs().mb_fwd == 3 && base + NSF * stage <= 74 * 1024) { CALL(4, 3) } else { DHTS_C_DISPATCH(p, CALL) }
 #undef CALL
     } else {
-#define CALL(CC, MB) arz_rollout_fwd_reg_kernel<T, CC, MB, 0><<<grid, p.threads, p.smem, st>>>(r0, y0, u0, ghost, nullptr, dx, umax, dt, B, N, steps, K, p.lpc, RollK(), ckpt, rT, yT, uT, flags);
+#define CALL(CC, MB) arz_rollout_fwd_reg_kernel<T, CC, MB, 0><<<grid, p.threads, p.smem, st>>>(r0, y0, u0, ghost, nullptr, dx, umax, kall, dt, B, N, steps, K, p.lpc, RollK(), ckpt, rT, yT, uT, flags);
         DHTS_C_DISPATCH(p, CALL)
 #undef CALL
     }
@@ -978,12 +998,16 @@ template <typename T> static long long rollout_scratch_elems(int B, int N, int K
 }
 
 template <typename T>
-static int rollout_bwd(const T* ckpt, const T* u0, const T* ghost, const T* ghost_t, const T* dx, const T* umax, T dt, int B,
+static int rollout_bwd(const T* ckpt, const T* u0, const T* ghost, const T* ghost_t, const T* dx, const T* umax, T dx_all,
+                       T umax_all, T dt, int B,
                        int N, int steps, int K, int xmode, const T* rT, const T* yT, const T* g_rT, const T* g_yT, const T* g_uT,
                        const T* g_hist, T* scratch, long long scratch_elems, T* g_r0, T* g_y0, T* g_ghost, T* g_ghost_t,
                        int* flags, cudaStream_t st) {
-    if (!ckpt || (!ghost && !ghost_t) || !dx || !umax || !g_r0 || !g_y0 || !flags || (!scratch && K > 1) || B < 0 || N < 1 || steps < 0 || K < 1)
+    if (!ckpt || (!ghost && !ghost_t) || (!dx != !umax) || !g_r0 || !g_y0 || !flags || (!scratch && K > 1) || B < 0 || N < 1 || steps < 0 || K < 1)
         return DHTS_ERR_INVALID;
+    const bool uni = !dx;
+    if (uni && !(dx_all > T(0) && umax_all > T(0))) return DHTS_ERR_INVALID;
+    const LaneK<T> kall = make_lanek<T>(uni ? umax_all : T(1), uni ? dx_all : T(1), dt);
     const bool ext = ghost_t || g_hist;
     if (ext && K != 1) return DHTS_ERR_INVALID;        // per-step ghosts / per-step adjoints need every state stored
     if (g_uT && (!rT || !yT)) return DHTS_ERR_INVALID;
@@ -1005,11 +1029,24 @@ static int rollout_bwd(const T* ckpt, const T* u0, const T* ghost, const T* ghos
         const long long g = (long long)sm_count_r() * (occ < 1 ? 1 : occ);                                             \
         grid = (int)(g < p.grid ? g : p.grid);                                                                         \
         arz_rollout_bwd_reg_kernel<T, CC, MB, 0, false, true><<<grid, p.threads, p.smem, st>>>(                           \
-            ckpt, u0, ghost, nullptr, nullptr, nullptr, dx, umax, dt, B, N, steps, K, p.lpc, rT, yT, g_rT, g_yT, g_uT, \
+            ckpt, u0, ghost, nullptr, nullptr, nullptr, dx, umax, kall, dt, B, N, steps, K, p.lpc, rT, yT, g_rT, g_yT, g_uT, \
             scratch, g_r0, g_y0, g_ghost, flags, p.ring_ns, make_rollk<T>(B, N, CC, p.lpc, p.threads / 32, false, true)); \
     }
-        if (p.C == 8) { CALL(8, 2) } else if (p.C == 4) { CALL(4, 2) } else { CALL(2, 2) }
+#define CALLU(CC, MB)                                                                                                  \
+    {                                                                                                                  \
+        cudaFuncSetAttribute(arz_rollout_bwd_reg_kernel<T, CC, MB, 0, false, true, true>,                              \
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);                                \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, arz_rollout_bwd_reg_kernel<T, CC, MB, 0, false, true, true>, \
+                                                      p.threads, p.smem);                                              \
+        const long long g = (long long)sm_count_r() * (occ < 1 ? 1 : occ);                                             \
+        grid = (int)(g < p.grid ? g : p.grid);                                                                         \
+        arz_rollout_bwd_reg_kernel<T, CC, MB, 0, false, true, true><<<grid, p.threads, p.smem, st>>>(                  \
+            ckpt, u0, ghost, nullptr, nullptr, nullptr, dx, umax, kall, dt, B, N, steps, K, p.lpc, rT, yT, g_rT, g_yT, g_uT, \
+            scratch, g_r0, g_y0, g_ghost, flags, p.ring_ns, make_rollk<T>(B, N, CC, p.lpc, p.threads / 32, false, true)); \
+    }
+        if (p.C == 8) { CALL(8, 2) } else if (p.C == 4) { if (uni && knobs().uni) { CALLU(4, 2) } else { CALL(4, 2) } } else { CALL(2, 2) }
 #undef CALL
+#undef CALLU
         return status_r();
     }
     RegPlan p;
@@ -1023,7 +1060,7 @@ static int rollout_bwd(const T* ckpt, const T* u0, const T* ghost, const T* ghos
     if (ext) {
 #define CALL(CC, MB)                                                                                                   \
     arz_rollout_bwd_reg_kernel<T, CC, MB, 1, true><<<grid, p.threads, p.smem, st>>>(                                   \
-        ckpt, u0, ghost_t ? nullptr : ghost, ghost_t, g_hist, g_ghost_t, dx, umax, dt, B, N, steps, K, p.lpc, rT, yT,  \
+        ckpt, u0, ghost_t ? nullptr : ghost, ghost_t, g_hist, g_ghost_t, dx, umax, kall, dt, B, N, steps, K, p.lpc, rT, yT,  \
         g_rT, g_yT, g_uT, scratch, g_r0, g_y0, g_ghost, flags, 0, RollK());
         DHTS_C_DISPATCH(p, CALL)
 #undef CALL
@@ -1035,7 +1072,7 @@ static int rollout_bwd(const T* ckpt, const T* u0, const T* ghost, const T* ghos
             cudaFuncSetAttribute(arz_rollout_bwd_reg_kernel<T, CC, MB, MD>,                                            \
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);                            \
         arz_rollout_bwd_reg_kernel<T, CC, MB, MD><<<grid, p.threads, p.smem, st>>>(                                    \
-            ckpt, u0, ghost, nullptr, nullptr, nullptr, dx, umax, dt, B, N, steps, K, p.lpc, rT, yT, g_rT, g_yT, g_uT, \
+            ckpt, u0, ghost, nullptr, nullptr, nullptr, dx, umax, kall, dt, B, N, steps, K, p.lpc, rT, yT, g_rT, g_yT, g_uT, \
             scratch, g_r0, g_y0, g_ghost, flags, p.ring_ns, make_rollk<T>(B, N, CC, p.lpc, p.threads / 32, false, false)); \
     }
     DHTS_CM_DISPATCH(p)
@@ -1047,10 +1084,10 @@ static int rollout_bwd(const T* ckpt, const T* u0, const T* ghost, const T* ghos
 
 #define DHTS_ARZ_ROLLOUT_API(SUF, T)                                                                                   \
     DHTS_EXPORT int dhts_arz_rollout_fwd_##SUF(const T* r0, const T* y0, const T* u0, const T* ghost, const T* ghost_t, \
-                                               const T* dx, const T* umax, T dt, int B, int N, int steps,              \
-                                               int ckpt_every, int ckpt_mode, T* ckpt, T* rT, T* yT, T* uT,            \
+                                               const T* dx, const T* umax, T dx_all, T umax_all, T dt, int B, int N,   \
+                                               int steps, int ckpt_every, int ckpt_mode, T* ckpt, T* rT, T* yT, T* uT, \
                                                int* flags, void* stream) {                                             \
-        return dhts::rollout_fwd<T>(r0, y0, u0, ghost, ghost_t, dx, umax, dt, B, N, steps, ckpt_every, ckpt_mode,      \
+        return dhts::rollout_fwd<T>(r0, y0, u0, ghost, ghost_t, dx, umax, dx_all, umax_all, dt, B, N, steps, ckpt_every, ckpt_mode, \
                                     ckpt, rT, yT, uT, flags, (cudaStream_t)stream);                                    \
     }                                                                                                                  \
     DHTS_EXPORT long long dhts_arz_rollout_ckpt_elems_##SUF(int B, int N, int steps, int ckpt_every, int* ckpt_mode) { \
@@ -1060,13 +1097,13 @@ static int rollout_bwd(const T* ckpt, const T* u0, const T* ghost, const T* ghos
         return dhts::rollout_scratch_elems<T>(B, N, ckpt_every);                                                       \
     }                                                                                                                  \
     DHTS_EXPORT int dhts_arz_rollout_bwd_##SUF(const T* ckpt, const T* u0, const T* ghost, const T* ghost_t,           \
-                                               const T* dx, const T* umax, T dt, int B, int N, int steps,              \
+                                               const T* dx, const T* umax, T dx_all, T umax_all, T dt, int B, int N, int steps, \
                                                int ckpt_every, int ckpt_mode, const T* rT, const T* yT,                \
                                                const T* g_rT, const T* g_yT, const T* g_uT, const T* g_hist,           \
                                                T* scratch,                                                             \
                                                long long scratch_elems, T* g_r0, T* g_y0, T* g_ghost, T* g_ghost_t,    \
                                                int* flags, void* stream) {                                             \
-        return dhts::rollout_bwd<T>(ckpt, u0, ghost, ghost_t, dx, umax, dt, B, N, steps, ckpt_every, ckpt_mode, rT,    \
+        return dhts::rollout_bwd<T>(ckpt, u0, ghost, ghost_t, dx, umax, dx_all, umax_all, dt, B, N, steps, ckpt_every, ckpt_mode, rT, \
                                     yT, g_rT, g_yT, g_uT, g_hist, scratch, scratch_elems, g_r0, g_y0, g_ghost, g_ghost_t, flags, \
                                     (cudaStream_t)stream);                                                             \
     }

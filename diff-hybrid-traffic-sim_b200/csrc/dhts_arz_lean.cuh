@@ -43,7 +43,7 @@ template <typename T> struct LaneK {
     T v4, vmax, veps;                  // V/4, V = dx/dt, V * 1e-5
 };
 
-template <typename T> __device__ __forceinline__ LaneK<T> make_lanek(T umax, T dx, T dt) {
+template <typename T> __host__ __device__ __forceinline__ LaneK<T> make_lanek(T umax, T dx, T dt) {
     LaneK<T> k;
     k.umax = umax; k.inv_umax = T(1) / umax; k.inv15 = T(1) / (T(1.5) * umax); k.dx = dx; k.cc = dt / dx;
     k.hum = T(0.5) * umax;

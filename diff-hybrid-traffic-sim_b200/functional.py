@@ -53,19 +53,23 @@ def arz_rollout(r0, u0, ghost_r, ghost_u, dx, umax, dt, steps, ckpt_every=32, fl
     it must stay untouched until this rollout's backward has run (see arz_rollout_plan)."""
     B, N = r0.shape
     flags = flags or _lib.Flags(r0.device)
-    dxl = _per_lane(dx, B, r0); uml = _per_lane(umax, B, r0)
-    um = uml[:, None]
+    # one geometry for all lanes (Python scalars: what the reference's drivers build) travels as two scalars
+    uni = not torch.is_tensor(dx) and not torch.is_tensor(umax)
+    dxl = None if uni else _per_lane(dx, B, r0); uml = None if uni else _per_lane(umax, B, r0)
+    um = float(umax) if uni else uml[:, None]
     y0 = compute_y(r0, u0, um)                       # set_r_u, _arz.py:82-86 (autograd, true derivative)
     ghost = torch.stack([ghost_r, compute_y(ghost_r, ghost_u, um), ghost_u.detach()], dim=-1)   # from_r_u, :74-80
     try:
-        out = ArzRolloutFn.apply(r0, y0, u0.detach(), ghost, dxl, uml, dt, steps, ckpt_every, flags.t, ckpt_buffer,
-                                 bool(return_history))
+        out = ArzRolloutFn.apply(r0, y0, u0.detach(), ghost, float(dx) if uni else dxl, float(umax) if uni else uml, dt, steps,
+                                 ckpt_every, flags.t, ckpt_buffer, bool(return_history))
         if return_history:
             return out[0], out[1], out[2], out[3][:, 0], out[3][:, 1]
         return out
     except _lib.UnsupportedShape:
         pass
     # lane too long for the register-resident kernel: chain the tiled per-step kernels (still CUDA)
+    if uni:
+        dxl = _per_lane(dx, B, r0); uml = _per_lane(umax, B, r0)
     r, y, u = r0, y0, u0.detach()
     hist = []
     for t in range(int(steps)):

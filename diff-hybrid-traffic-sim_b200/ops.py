@@ -121,12 +121,21 @@ class ArzRolloutFn(torch.autograd.Function):
     ghost [B,2,3]: static ghost cells (r, y, u); ghost [steps,B,2,3]: one pair of ghost cells PER STEP (a lane inside
     a network, road_network.py:364-387).  want_hist (needs ckpt_every = 1): a fourth output hist [steps,2,B,N], the
     (r, y) state BEFORE every step (hist[0] = the input) -- the kernels' checkpoint tensor itself -- so that a loss
-    may read the lane at every step; its gradient is injected step by step in the adjoint kernel."""
+    may read the lane at every step; its gradient is injected step by step in the adjoint kernel.
+    dx, umax: tensors [B], or two Python floats when every lane has the same geometry (include/dhts.h: dx = umax = NULL
+    with dx_all / umax_all -- the kernels then read the lane constants from their parameter block)."""
 
     @staticmethod
     def forward(ctx, r0, y0, u0, ghost, dx, umax, dt, steps, ckpt_every, flags, ckpt_buffer=None, want_hist=False):
-        dev = _lib.require_cuda(r0, y0, u0, ghost, dx, umax, flags)
-        r0, y0, u0, ghost, dx, umax = map(_c, (r0, y0, u0, ghost, dx, umax))
+        uni = not torch.is_tensor(dx) and not torch.is_tensor(umax)
+        if uni:
+            dev = _lib.require_cuda(r0, y0, u0, ghost, flags)
+            r0, y0, u0, ghost = map(_c, (r0, y0, u0, ghost))
+            dx_all, umax_all, dx, umax = float(dx), float(umax), None, None
+        else:
+            dev = _lib.require_cuda(r0, y0, u0, ghost, dx, umax, flags)
+            r0, y0, u0, ghost, dx, umax = map(_c, (r0, y0, u0, ghost, dx, umax))
+            dx_all = umax_all = 0.0
         B, N = r0.shape
         dt_, steps, K = float(dt), int(steps), max(1, int(ckpt_every))
         tv = ghost.dim() == 4
@@ -154,21 +163,26 @@ class ArzRolloutFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             check(_fn("arz_rollout_fwd", r0.dtype)(ptr(r0), ptr(y0), ptr(u0), ptr(None if tv else ghost),
                                                    ptr(ghost if tv else None), ptr(dx), ptr(umax),
+                                                   creal(r0.dtype, dx_all), creal(r0.dtype, umax_all),
                                                    creal(r0.dtype, dt_), B, N, steps, K, xmode, ptr(ckpt), ptr(rT), ptr(yT),
                                                    ptr(uT), ptr(flags), stream_ptr(dev)), "dhts_arz_rollout_fwd")
         if need_grad:
-            ctx.save_for_backward(ckpt, u0, ghost, dx, umax, rT, yT)
+            if uni:
+                ctx.save_for_backward(ckpt, u0, ghost, rT, yT)
+            else:
+                ctx.save_for_backward(ckpt, u0, ghost, rT, yT, dx, umax)
         ctx.flags = flags
-        ctx.cfg = (dt_, steps, K, B, N, tv, bool(want_hist), xmode)
+        ctx.cfg = (dt_, steps, K, B, N, tv, bool(want_hist), xmode, dx_all, umax_all)
         if want_hist:
             return rT, yT, uT, ckpt.view(S, 2, B, N)
         return rT, yT, uT
 
     @staticmethod
     def backward(ctx, g_rT, g_yT, g_uT, g_hist=None):
-        ckpt, u0, ghost, dx, umax, rT, yT = ctx.saved_tensors
+        ckpt, u0, ghost, rT, yT = ctx.saved_tensors[:5]
+        dx, umax = ctx.saved_tensors[5:] if len(ctx.saved_tensors) > 5 else (None, None)
         flags = ctx.flags
-        dt_, steps, K, B, N, tv, want_hist, xmode = ctx.cfg
+        dt_, steps, K, B, N, tv, want_hist, xmode, dx_all, umax_all = ctx.cfg
         dev, dtype = ghost.device, ghost.dtype
         g_rT, g_yT, g_uT, g_hist = map(_c, (g_rT, g_yT, g_uT, g_hist))
         g_r0 = torch.empty((B, N), dtype=dtype, device=dev)
@@ -180,7 +194,8 @@ class ArzRolloutFn(torch.autograd.Function):
                 raise _lib.UnsupportedShape("dhts_arz_rollout_bwd: lane does not fit the fused kernel")
             scratch = torch.empty((max(int(n), 1),), dtype=dtype, device=dev)
             check(_fn("arz_rollout_bwd", dtype)(ptr(ckpt), ptr(u0), ptr(None if tv else ghost), ptr(ghost if tv else None),
-                                                ptr(dx), ptr(umax), creal(dtype, dt_), B, N, steps, K, xmode, ptr(rT), ptr(yT),
+                                                ptr(dx), ptr(umax), creal(dtype, dx_all), creal(dtype, umax_all),
+                                                creal(dtype, dt_), B, N, steps, K, xmode, ptr(rT), ptr(yT),
                                                 ptr(g_rT), ptr(g_yT), ptr(g_uT), ptr(g_hist), ptr(scratch),
                                                 ctypes.c_longlong(int(n)), ptr(g_r0), ptr(g_y0),
                                                 ptr(None if tv else g_gh), ptr(g_gh if tv else None), ptr(flags),

@@ -99,6 +99,9 @@ int dhts_arz_step_bwd_f32(const float* r_pad, const float* y_pad, const float* u
  * own it for the whole rollout (1, 2, 4 or 8 consecutive cells per thread).
  *   r0, y0 [B][N]; u0 [B][N] or NULL (stored speed of the initial cells, set_r_u)
  *   ghost [B][2][3]        (r, y, u) of the left / right ghost cell
+ *   dx, umax [B]           cell length / speed limit per lane (MacroLane.cell_length, .speed_limit), or BOTH NULL: every
+ *                          lane has dx_all / umax_all (what the reference's drivers build: one lane shape per problem) --
+ *                          the kernels then read the lane constants from their parameter block instead of registers
  *   ckpt [S][2][B][N] (+ outcomes) or NULL, S = ceil(steps/ckpt_every): state BEFORE steps
  *                          0, K, 2K, ... (needed by the backward entry point)
  *   ckpt_mode              0: ckpt holds the states only.  1: behind the S states it also holds the OUTCOME of every
@@ -118,13 +121,13 @@ int dhts_arz_step_bwd_f32(const float* r_pad, const float* y_pad, const float* u
  * dhts_idm_rollout_max_ckpt_every() = 32, with the same fallback.
  */
 int dhts_arz_rollout_fwd_f64(const double* r0, const double* y0, const double* u0, const double* ghost,
-                             const double* ghost_t, const double* dx, const double* umax, double dt, int B, int N,
-                             int steps, int ckpt_every, int ckpt_mode, double* ckpt, double* rT, double* yT, double* uT,
-                             int* flags, void* stream);
+                             const double* ghost_t, const double* dx, const double* umax, double dx_all, double umax_all,
+                             double dt, int B, int N, int steps, int ckpt_every, int ckpt_mode, double* ckpt, double* rT,
+                             double* yT, double* uT, int* flags, void* stream);
 int dhts_arz_rollout_fwd_f32(const float* r0, const float* y0, const float* u0, const float* ghost,
-                             const float* ghost_t, const float* dx, const float* umax, float dt, int B, int N,
-                             int steps, int ckpt_every, int ckpt_mode, float* ckpt, float* rT, float* yT, float* uT,
-                             int* flags, void* stream);
+                             const float* ghost_t, const float* dx, const float* umax, float dx_all, float umax_all,
+                             float dt, int B, int N, int steps, int ckpt_every, int ckpt_mode, float* ckpt, float* rT,
+                             float* yT, float* uT, int* flags, void* stream);
 
 /* Adjoint of the rollout: the chain of dMacroForwardLayer.backward calls autograd makes for the T steps
  * (road/lane/dmacro_lane.py:277-310), flux-difference form, no stored Jacobian band.
@@ -142,13 +145,13 @@ int dhts_arz_rollout_fwd_f32(const float* r0, const float* y0, const float* u0, 
  *                           the ITSCP queue length, example/control/itscp/_env.py:662-742, on independent lanes)
  */
 int dhts_arz_rollout_bwd_f64(const double* ckpt, const double* u0, const double* ghost, const double* ghost_t,
-                             const double* dx, const double* umax, double dt, int B, int N, int steps, int ckpt_every,
-                             int ckpt_mode, const double* rT, const double* yT, const double* g_rT, const double* g_yT,
+                             const double* dx, const double* umax, double dx_all, double umax_all, double dt, int B, int N,
+                             int steps, int ckpt_every, int ckpt_mode, const double* rT, const double* yT, const double* g_rT, const double* g_yT,
                              const double* g_uT, const double* g_hist, double* scratch, long long scratch_elems,
                              double* g_r0, double* g_y0, double* g_ghost, double* g_ghost_t, int* flags, void* stream);
 int dhts_arz_rollout_bwd_f32(const float* ckpt, const float* u0, const float* ghost, const float* ghost_t,
-                             const float* dx, const float* umax, float dt, int B, int N, int steps, int ckpt_every,
-                             int ckpt_mode, const float* rT, const float* yT, const float* g_rT, const float* g_yT, const float* g_uT,
+                             const float* dx, const float* umax, float dx_all, float umax_all, float dt, int B, int N,
+                             int steps, int ckpt_every, int ckpt_mode, const float* rT, const float* yT, const float* g_rT, const float* g_yT, const float* g_uT,
                              const float* g_hist, float* scratch, long long scratch_elems, float* g_r0, float* g_y0,
                              float* g_ghost, float* g_ghost_t, int* flags, void* stream);
 long long dhts_arz_rollout_scratch_elems_f64(int B, int N, int ckpt_every);

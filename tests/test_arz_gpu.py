@@ -185,6 +185,31 @@ def test_rollout_with_vacuum_vs_oracle(dev, B, N, T, K):
     assert relerr(torch.stack([tgr.grad, tgu.grad], -1).cpu(), o["g_ghost"]) < 1e-8
 
 
+@pytest.mark.parametrize("B,N,T,K", [(9, 1024, 14, 1), (300, 1024, 5, 1), (9, 1024, 14, 8), (37, 10, 30, 8), (21, 128, 9, 1)])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_rollout_uniform_geometry_equals_per_lane_arrays(dev, dtype, B, N, T, K):
+    """dx / umax given as two scalars (include/dhts.h: dx = umax = NULL, dx_all / umax_all -- every lane of the reference's
+    drivers has the same cell length and speed limit) select kernels that read the lane constants from their parameter
+    block; the arithmetic is the same, so states and gradients equal the per-lane-array call BITWISE."""
+    import dhts_b200
+    from dhts_b200 import functional as F
+    g = torch.Generator(device=dev).manual_seed(B * 31 + N)
+    rnd = lambda *s: torch.rand(s, generator=g, dtype=dtype, device=dev)
+    r0, u0, gr, gu = rnd(B, N), rnd(B, N) * 30, rnd(B, 2), rnd(B, 2) * 30
+    w = torch.randn((B, N), generator=g, dtype=dtype, device=dev)
+    flags = dhts_b200.Flags(dev)
+    outs = []
+    for dx, um in ((5.0, 30.0), (torch.full((B,), 5.0, dtype=dtype, device=dev), torch.full((B,), 30.0, dtype=dtype, device=dev))):
+        a = r0.clone().requires_grad_(); b = u0.clone().requires_grad_()
+        c = gr.clone().requires_grad_(); d = gu.clone().requires_grad_()
+        rT, yT, uT = F.arz_rollout(a, b, c, d, dx, um, 0.01, T, ckpt_every=K, flags=flags)
+        ((rT * w).sum() + (uT * w).sum() / 30).backward()
+        outs.append((rT.detach(), yT.detach(), uT.detach(), a.grad, b.grad, c.grad, d.grad))
+    flags.check()
+    for x, y in zip(*outs):
+        assert torch.equal(x, y)
+
+
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
 def test_rollout_tma_paths_equal_plain_paths(dev, dtype):
     """Every state stored: the forward's staged TMA bulk stores (shared-memory staging ring, cp.async.bulk to HBM) and
