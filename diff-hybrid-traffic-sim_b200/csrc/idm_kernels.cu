@@ -184,12 +184,15 @@ __device__ __forceinline__ int lane_step(WarpLane<T, VPT>& w, T head_dp, T head_
     return ncol;
 }
 
-template <typename T, int VPT>
+// EXT = false: no per-step head deltas (head_t is null) -- a separate instantiation, so that the plain rollout does not carry the
+// per-step fetches and tests in its time loop (they cost 9 % when they were run-time branches).
+template <typename T, int VPT, bool EXT>
 __global__ void __launch_bounds__(IDM_ROLL_BLOCK)
 idm_rollout_fwd_kernel(const T* __restrict__ p0, const T* __restrict__ v0, const T* __restrict__ params,
-                       const int* __restrict__ lane_off, const T* __restrict__ head, const T* __restrict__ head_t, T dt,
+                       const int* __restrict__ lane_off, const T* __restrict__ head, const T* __restrict__ head_t_, T dt,
                        int V, int L, int steps, int K, T* __restrict__ ckpt, T* __restrict__ pT, T* __restrict__ vT,
                        int* __restrict__ flags) {
+    const T* __restrict__ head_t = EXT ? head_t_ : nullptr;
     const unsigned lane = threadIdx.x & 31;
     const int wid = (blockIdx.x * IDM_ROLL_BLOCK + threadIdx.x) >> 5, nw = (gridDim.x * IDM_ROLL_BLOCK) >> 5;
     const T inv_dt = T(1) / dt;
@@ -221,13 +224,17 @@ idm_rollout_fwd_kernel(const T* __restrict__ p0, const T* __restrict__ v0, const
     if (ncol) { atomicOr(flags, FLAG_COLLISION); atomicAdd(flags + 1, ncol); }
 }
 
-template <typename T, int VPT>
+// EXT = false: no per-step head deltas, no per-step adjoint injection (head_t, g_head_t, g_hist are null).
+template <typename T, int VPT, bool EXT>
 __global__ void __launch_bounds__(IDM_ROLL_BLOCK)
 idm_rollout_bwd_kernel(const T* __restrict__ ckpt, const T* __restrict__ params, const int* __restrict__ lane_off,
-                       const T* __restrict__ head, const T* __restrict__ head_t, T dt, int V, int L, int steps, int K,
-                       const T* __restrict__ g_pT, const T* __restrict__ g_vT, const T* __restrict__ g_hist,
-                       T* __restrict__ g_p0, T* __restrict__ g_v0, T* __restrict__ g_head, T* __restrict__ g_head_t,
+                       const T* __restrict__ head, const T* __restrict__ head_t_, T dt, int V, int L, int steps, int K,
+                       const T* __restrict__ g_pT, const T* __restrict__ g_vT, const T* __restrict__ g_hist_,
+                       T* __restrict__ g_p0, T* __restrict__ g_v0, T* __restrict__ g_head, T* __restrict__ g_head_t_,
                        int* __restrict__ flags) {
+    const T* __restrict__ head_t = EXT ? head_t_ : nullptr;
+    const T* __restrict__ g_hist = EXT ? g_hist_ : nullptr;
+    T* __restrict__ g_head_t = EXT ? g_head_t_ : nullptr;
     const unsigned lane = threadIdx.x & 31;
     const int wid = (blockIdx.x * IDM_ROLL_BLOCK + threadIdx.x) >> 5, nw = (gridDim.x * IDM_ROLL_BLOCK) >> 5;
     const T inv_dt = T(1) / dt;
@@ -377,7 +384,8 @@ static int idm_rollout_fwd(const T* p0, const T* v0, const T* params, const int*
     if (V == 0 || L == 0) return DHTS_OK;
     int grid = idm_grid(L);
     if (K < 1) K = 1;
-#define CALL(VPT) idm_rollout_fwd_kernel<T, VPT><<<grid, IDM_ROLL_BLOCK, 0, st>>>(p0, v0, params, lane_off, head, head_t, dt, V, L, steps, K, ckpt, pT, vT, flags);
+#define CALL(VPT) { if (head_t) idm_rollout_fwd_kernel<T, VPT, true><<<grid, IDM_ROLL_BLOCK, 0, st>>>(p0, v0, params, lane_off, head, head_t, dt, V, L, steps, K, ckpt, pT, vT, flags); \
+                    else idm_rollout_fwd_kernel<T, VPT, false><<<grid, IDM_ROLL_BLOCK, 0, st>>>(p0, v0, params, lane_off, head, nullptr, dt, V, L, steps, K, ckpt, pT, vT, flags); }
     DHTS_VPT_DISPATCH(max_lane, CALL)
 #undef CALL
     return last_status_idm();
@@ -394,7 +402,8 @@ static int idm_rollout_bwd(const T* ckpt, const T* params, const int* lane_off, 
     if (K > IDM_KMAX) return DHTS_ERR_UNSUPPORTED;
     if (L == 0) return DHTS_OK;
     int grid = idm_grid(L);
-#define CALL(VPT) idm_rollout_bwd_kernel<T, VPT><<<grid, IDM_ROLL_BLOCK, 0, st>>>(ckpt, params, lane_off, head, head_t, dt, V, L, steps, K, g_pT, g_vT, g_hist, g_p0, g_v0, head_t ? nullptr : g_head, g_head_t, flags);
+#define CALL(VPT) { if (head_t || g_hist || g_head_t) idm_rollout_bwd_kernel<T, VPT, true><<<grid, IDM_ROLL_BLOCK, 0, st>>>(ckpt, params, lane_off, head, head_t, dt, V, L, steps, K, g_pT, g_vT, g_hist, g_p0, g_v0, head_t ? nullptr : g_head, g_head_t, flags); \
+                    else idm_rollout_bwd_kernel<T, VPT, false><<<grid, IDM_ROLL_BLOCK, 0, st>>>(ckpt, params, lane_off, head, nullptr, dt, V, L, steps, K, g_pT, g_vT, nullptr, g_p0, g_v0, g_head, nullptr, flags); }
     DHTS_VPT_DISPATCH(max_lane, CALL)
 #undef CALL
     return last_status_idm();
