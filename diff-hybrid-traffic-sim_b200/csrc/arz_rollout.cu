@@ -260,7 +260,9 @@ __device__ __forceinline__ FRec<T> fcell(T r, T y, T us, const LaneK<T>& k) {
 // XR: also store the outcome of every interface (dhts_arz_lean.cuh) as warp BALLOTS: for the interface on the left of cell c
 // of every thread of the warp, xs[c] = (ballot of Q_L, ballot of Q_M) -- one vote per bit and one 8-byte store by lane 0
 // instead of per-thread bit assembly; the adjoint (same thread -> cell mapping) tests its lane's bit.
-template <typename T, int C, bool STORED, bool CHECK, bool VAC, bool XR>
+// DEFER (with CHECK): the sufficient CFL tests of the cells are only AND-ed into okL -- no vote, no branch inside the sweep (one
+// basic block); the caller votes once per step and runs the exact test from the stored state (cfl_exact_rows).
+template <typename T, int C, bool STORED, bool CHECK, bool VAC, bool XR, bool DEFER = false>
 __device__ __forceinline__ bool chunk_fwd_sweep(T* r, T* y, const T* us, const FRec<T>& last, FRec<T>& L,
                                                 const LaneK<T>& k, T dt, T* f0, T& fpr, T& fpy, bool& okL, uint2* xs,
                                                 unsigned lane) {
@@ -277,10 +279,13 @@ __device__ __forceinline__ bool chunk_fwd_sweep(T* r, T* y, const T* us, const F
         } else fflux<T, VAC>(L, cur.r, cur.us, k, fr, fy);
         if (CHECK) {
             const bool okR = cell_speed_ok(cur.us, cur.w, k);
-            // never in a valid run; the vote makes the branch warp-uniform (no reconvergence bookkeeping around it): every
-            // lane then evaluates the exact test, which is what the flag means anyway
-            if (__any_sync(FULL, !okL | !okR)) bad |= cfl_exact_bad(L.r, L.us, L.sq, L.w, cur.r, cur.us, k, dt);
-            okL = okR;
+            if (DEFER) okL &= okR;
+            else {
+                // never in a valid run; the vote makes the branch warp-uniform (no reconvergence bookkeeping around it): every
+                // lane then evaluates the exact test, which is what the flag means anyway
+                if (__any_sync(FULL, !okL | !okR)) bad |= cfl_exact_bad(L.r, L.us, L.sq, L.w, cur.r, cur.us, k, dt);
+                okL = okR;
+            }
         }
         if (c == 0) { f0[0] = fr; f0[1] = fy; }
         else {
@@ -293,7 +298,8 @@ __device__ __forceinline__ bool chunk_fwd_sweep(T* r, T* y, const T* us, const F
 }
 
 // xs (XR): the C outcome ballot pairs of this thread's WARP in the step's stage of the staging ring.
-template <typename T, int C, bool STORED, bool CHECK, bool XR = false>
+// DEFER: returns "a sufficient CFL test failed at a cell this thread's interfaces touch" instead of the exact verdict.
+template <typename T, int C, bool STORED, bool CHECK, bool XR = false, bool DEFER = false>
 __device__ __forceinline__ bool chunk_fwd_step(T* r, T* y, const T* us, bool first_chunk, bool last_chunk,
                                                const LaneK<T>& k, const T* ghostL, const T* ghostR, T dt, T* boxL,
                                                T* boxR, int warp, int nwarp, unsigned lane, uint2* xs = nullptr) {
@@ -309,8 +315,8 @@ __device__ __forceinline__ bool chunk_fwd_step(T* r, T* y, const T* us, bool fir
     T f0[2], fpr = T(0), fpy = T(0);
     bool bad;
     anyvac = __any_sync(FULL, anyvac);            // one variant per warp (a mixed warp would run both, one after the other)
-    if (__builtin_expect(anyvac, 0)) bad = chunk_fwd_sweep<T, C, STORED, CHECK, true, XR>(r, y, us, last, L, k, dt, f0, fpr, fpy, okL, xs, lane);
-    else bad = chunk_fwd_sweep<T, C, STORED, CHECK, false, XR>(r, y, us, last, L, k, dt, f0, fpr, fpy, okL, xs, lane);
+    if (__builtin_expect(anyvac, 0)) bad = chunk_fwd_sweep<T, C, STORED, CHECK, true, XR, DEFER>(r, y, us, last, L, k, dt, f0, fpr, fpy, okL, xs, lane);
+    else bad = chunk_fwd_sweep<T, C, STORED, CHECK, false, XR, DEFER>(r, y, us, last, L, k, dt, f0, fpr, fpy, okL, xs, lane);
     // (XR) the outcomes went into the step's stage; this fence -- before the step's second block barrier, after which the bulk
     // store is issued -- also covers the (r, y) rows written at the top of the step
     if (XR) fence_proxy_async();
@@ -320,11 +326,40 @@ __device__ __forceinline__ bool chunk_fwd_step(T* r, T* y, const T* us, bool fir
         const FRec<T> G = unpack_f(ghostR);
         fflux<T, true>(L, G.r, G.us, k, fR[0], fR[1]);
         if (CHECK) {
-            if (!okL || !cell_speed_ok(G.us, G.w, k)) bad |= cfl_exact_bad(L.r, L.us, L.sq, L.w, G.r, G.us, k, dt);
+            if (DEFER) okL &= cell_speed_ok(G.us, G.w, k);
+            else if (!okL || !cell_speed_ok(G.us, G.w, k)) bad |= cfl_exact_bad(L.r, L.us, L.sq, L.w, G.r, G.us, k, dt);
         }
     }
     r[C - 1] = fma(fpr - fR[0], k.cc, r[C - 1]);
     y[C - 1] = fma(fpy - fR[1], k.cc, y[C - 1]);
+    return (CHECK && DEFER) ? !okL : bad;
+}
+
+// The exact CFL test of one step (_macro_lane.py:137-146) for the interfaces this thread owns -- the one on the left of each of
+// its cells, plus the right ghost's for the last chunk -- evaluated from the state BEFORE the step as the staged forward kernel
+// keeps it in shared memory (lr, ly: the lane's rows in the step's stage; lu: the stored speeds of step 0 or null).  Only run
+// after a sufficient per-cell test failed somewhere in the warp, i.e. never in a run the reference would accept.
+template <typename T, int C>
+__device__ __noinline__ bool cfl_exact_rows(const T* lr, const T* ly, const T* lu, int kc, bool last_chunk, const LaneK<T>& k,
+                                            const T* ghostL, const T* ghostR, T dt) {
+    bool bad = false;
+    for (int c = 0; c <= C; c++) {
+        if (c == C && !last_chunk) break;
+        const int i = kc * C + c;                 // interface between cell i - 1 and cell i (i == N: the right ghost)
+        FRec<T> L;
+        if (i == 0) L = unpack_f(ghostL);
+        else {
+            L = lu ? fderive<T, true>(lr[i - 1], ly[i - 1], lu[i - 1], k) : fderive<T, false>(lr[i - 1], ly[i - 1], T(0), k);
+            if (lr[i - 1] < DHTS_EPS) L.w = w_vacuum(lr[i - 1], L.us, k);
+        }
+        T Rr, Rus;
+        if (c == C) { const FRec<T> G = unpack_f(ghostR); Rr = G.r; Rus = G.us; }
+        else {
+            const FRec<T> R = lu ? fderive<T, true>(lr[i], ly[i], lu[i], k) : fderive<T, false>(lr[i], ly[i], T(0), k);
+            Rr = R.r; Rus = R.us;
+        }
+        bad |= cfl_exact_bad(L.r, L.us, L.sq, L.w, Rr, Rus, k, dt);
+    }
     return bad;
 }
 
@@ -419,12 +454,16 @@ __global__ void __launch_bounds__(1024 / (C < 4 ? C : 4), MB) arz_rollout_fwd_re
                 if (active) { store_chunk<T, C>(sp, r); store_chunk<T, C>(sp + rk.y_off, y); }
                 if (!XR) fence_proxy_async();
                 if (threadIdx.x == 0) bulk_wait_read<(NS > 2 ? NS - 2 : 0)>();
+                bool sus;       // a sufficient CFL test failed: the exact one runs from the stage's rows (the state before the step)
                 if (t == 0 && u0) {
                     T us[C];
                     load_chunk<T, C>(u0 + off, us);
-                    lbad |= chunk_fwd_step<T, C, true, true, XR>(r, y, us, first_chunk, last_chunk, k, gL, gR, dt, bl, br, warp, nwarp, lane, sx);
+                    sus = chunk_fwd_step<T, C, true, true, XR, true>(r, y, us, first_chunk, last_chunk, k, gL, gR, dt, bl, br, warp, nwarp, lane, sx);
                 } else
-                    lbad |= chunk_fwd_step<T, C, false, true, XR>(r, y, nullptr, first_chunk, last_chunk, k, gL, gR, dt, bl, br, warp, nwarp, lane, sx);
+                    sus = chunk_fwd_step<T, C, false, true, XR, true>(r, y, nullptr, first_chunk, last_chunk, k, gL, gR, dt, bl, br, warp, nwarp, lane, sx);
+                if (__builtin_expect(__any_sync(FULL, sus), 0))
+                    lbad |= cfl_exact_rows<T, C>(sp - kc * C, sp - kc * C + rk.y_off, (t == 0 && u0) ? u0 + (size_t)(lane0 + ll) * N : nullptr,
+                                                 kc, last_chunk, k, gL, gR, dt);
                 bl += flipl; flipl = -flipl; br += flipr; flipr = -flipr;
                 // every thread has passed the step's block barriers: the stage is complete and fenced
                 if (threadIdx.x == 0) {     // thread 0: soff == 0, sp is the stage
