@@ -30,6 +30,7 @@
 // ghosts, runs the flux-difference adjoint over its cells, pulls the ghost adjoint back through from_r_u and the
 // blend, and publishes (d green, d signal) per side in shared memory; after one barrier each lane GATHERS what its
 // neighbours published for its edge cells and for its signal (fixed order: deterministic, no atomics).
+#include <cstdlib>
 #include <cuda_pipeline.h>
 #include "dhts_net_if.cuh"
 
@@ -150,8 +151,11 @@ __global__ void __launch_bounds__(512) net_rollout_fwd_kernel(NetArgs<T> a, cons
 // g_states [T][R][3][NC]  optional: dLoss/d(r, y, u) of the state AFTER step t (the last one is the terminal adjoint)
 // g_reward [R]            optional: dLoss/d reward (fused queue reward)
 // outputs: g_r0, g_y0, g_u0 [R][NC]; g_own0 [R][n_own][2]; g_sig, g_inc [R][T][L]
-template <typename T>
-__global__ void __launch_bounds__(512) net_rollout_bwd_kernel(NetArgs<T> a, const T* __restrict__ hist, const T* __restrict__ ownh,
+// MAXTH / MINB: launch bounds.  (512, 1): up to one thread per interface of a large network, 128 registers.  (256, 3): the
+// many-replica configuration (half as many threads as interfaces, several CTAs per SM hiding each other's barriers) at 80
+// registers -- no spills, three CTAs per SM instead of two.
+template <typename T, int MAXTH, int MINB>
+__global__ void __launch_bounds__(MAXTH, MINB) net_rollout_bwd_kernel(NetArgs<T> a, const T* __restrict__ hist, const T* __restrict__ ownh,
                                                                const T* __restrict__ g_states, const T* __restrict__ g_reward,
                                                                T* __restrict__ g_r0, T* __restrict__ g_y0, T* __restrict__ g_u0,
                                                                T* __restrict__ g_own0, T* __restrict__ g_sig,
@@ -385,10 +389,18 @@ static int net_bwd(const NetArgs<T>& a, const T* hist, const T* ownh, const T* g
     const int threads = net_threads(a.L, a.NC, a.R);
     const size_t smem = net_smem<T>(a.L, a.NC, a.n_own, true, threads);
     int grid = 1;
-    rc = net_launch_cfg<T>(net_rollout_bwd_kernel<T>, smem, threads, a.R, &grid);
-    if (rc) return rc;
-    net_rollout_bwd_kernel<T><<<grid, threads, smem, st>>>(a, hist, ownh, g_states, g_reward, g_r0, g_y0, g_u0, g_own0, g_sig,
-                                                           g_inc, flags);
+    static const bool occ3 = [] { const char* e = getenv("DHTS_NET_BWD_MINB"); return !e || atoi(e) != 1; }();
+    if (threads <= 256 && a.R > net_sm_count() && occ3) {
+        rc = net_launch_cfg<T>(net_rollout_bwd_kernel<T, 256, 3>, smem, threads, a.R, &grid);
+        if (rc) return rc;
+        net_rollout_bwd_kernel<T, 256, 3><<<grid, threads, smem, st>>>(a, hist, ownh, g_states, g_reward, g_r0, g_y0, g_u0, g_own0,
+                                                                       g_sig, g_inc, flags);
+    } else {
+        rc = net_launch_cfg<T>(net_rollout_bwd_kernel<T, 512, 1>, smem, threads, a.R, &grid);
+        if (rc) return rc;
+        net_rollout_bwd_kernel<T, 512, 1><<<grid, threads, smem, st>>>(a, hist, ownh, g_states, g_reward, g_r0, g_y0, g_u0, g_own0,
+                                                                       g_sig, g_inc, flags);
+    }
     return cudaGetLastError() == cudaSuccess ? DHTS_OK : DHTS_ERR_CUDA;
 }
 
