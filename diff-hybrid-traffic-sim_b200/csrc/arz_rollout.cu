@@ -21,6 +21,7 @@
 // road/lane/dmacro_lane.py:68-132,234-310).
 #include <cstdint>
 #include <cstdlib>
+#define DHTS_CONSTANT_BANK_LITERALS      // see dhts_arz.cuh (KC)
 #include "dhts_arz_lean.cuh"
 #include "dhts_api.h"
 

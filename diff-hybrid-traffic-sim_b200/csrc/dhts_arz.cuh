@@ -31,16 +31,23 @@ template <> __device__ __forceinline__ float t_sqrt<float>(float x) { return sqr
 __device__ __forceinline__ double t_abs(double x) { return fabs(x); }
 __device__ __forceinline__ float t_abs(float x) { return fabsf(x); }
 
-// fp64 constants that are not 32-bit immediates live in constant memory: an FP64 instruction takes a constant-bank operand for
-// free, whereas a literal costs two moves into a register pair every time the compiler rematerialises it (it does, under the
-// rollouts' register caps: ~20 of the adjoint's ~630 instructions per warp-step were such moves).
+// fp64 constants that are not 32-bit immediates can live in constant memory: an FP64 instruction takes a constant-bank operand
+// for free, whereas a literal costs two moves into a register pair every time the compiler rematerialises it (it does, under the
+// lane rollouts' register caps).  Only translation units that define DHTS_CONSTANT_BANK_LITERALS get this (arz_rollout.cu: the
+// forward sweep gains 2 %); elsewhere the compiler hoists the constant loads into registers instead -- the macro-network forward
+// kernel went from 62 to 104 registers and lost a third of its occupancy with it (r3f / r3k) -- so the default is literals.
+#ifdef DHTS_CONSTANT_BANK_LITERALS
 static __constant__ double dhts_kd[4] = {1e-5, 316.22776601683796 /* 1/sqrt(1e-5) */, 0.375, 0.5 / 1.5};
+#define DHTS_KD(i, lit) dhts_kd[i]
+#else
+#define DHTS_KD(i, lit) (lit)
+#endif
 template <typename T> struct KC;
 template <> struct KC<double> {
-    static __device__ __forceinline__ double eps() { return dhts_kd[0]; }
-    static __device__ __forceinline__ double rsqrt_eps() { return dhts_kd[1]; }
-    static __device__ __forceinline__ double c375() { return dhts_kd[2]; }
-    static __device__ __forceinline__ double third() { return dhts_kd[3]; }
+    static __device__ __forceinline__ double eps() { return DHTS_KD(0, 1e-5); }
+    static __device__ __forceinline__ double rsqrt_eps() { return DHTS_KD(1, 316.22776601683796); }
+    static __device__ __forceinline__ double c375() { return DHTS_KD(2, 0.375); }
+    static __device__ __forceinline__ double third() { return DHTS_KD(3, 0.5 / 1.5); }
 };
 template <> struct KC<float> {
     static __device__ __forceinline__ float eps() { return 1e-5f; }
@@ -58,7 +65,7 @@ template <> __device__ __forceinline__ double f_rsqrt<double>(double x) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     double e = fma(-(x * y), y, 1.0);                 // 1 - x y^2
-    return fma(y, e * fma(dhts_kd[2], e, 0.5), y);         // Halley step: error^3 -> below 1 ulp
+    return fma(y, e * fma(KC<double>::c375(), e, 0.5), y);         // Halley step: error^3 -> below 1 ulp
 }
 template <> __device__ __forceinline__ float f_rsqrt<float>(float x) { return rsqrtf(x); }
 // the same with the 0.375 as a literal (adjoint kernels: there the compiler does better with literals, see KC)
