@@ -37,7 +37,7 @@ __device__ __forceinline__ float t_abs(float x) { return fabsf(x); }
 // forward sweep gains 2 %); elsewhere the compiler hoists the constant loads into registers instead -- the macro-network forward
 // kernel went from 62 to 104 registers and lost a third of its occupancy with it (r3f / r3k) -- so the default is literals.
 #ifdef DHTS_CONSTANT_BANK_LITERALS
-static __constant__ double dhts_kd[4] = {1e-5, 316.22776601683796 /* 1/sqrt(1e-5) */, 0.375, 0.5 / 1.5};
+static __constant__ double dhts_kd[5] = {1e-5, 316.22776601683796 /* 1/sqrt(1e-5) */, 0.375, 0.5 / 1.5, 0.0031622776601683794 /* sqrt(1e-5) */};
 #define DHTS_KD(i, lit) dhts_kd[i]
 #else
 #define DHTS_KD(i, lit) (lit)
@@ -48,12 +48,14 @@ template <> struct KC<double> {
     static __device__ __forceinline__ double rsqrt_eps() { return DHTS_KD(1, 316.22776601683796); }
     static __device__ __forceinline__ double c375() { return DHTS_KD(2, 0.375); }
     static __device__ __forceinline__ double third() { return DHTS_KD(3, 0.5 / 1.5); }
+    static __device__ __forceinline__ double sqrt_eps() { return DHTS_KD(4, 0.0031622776601683794); }
 };
 template <> struct KC<float> {
     static __device__ __forceinline__ float eps() { return 1e-5f; }
     static __device__ __forceinline__ float rsqrt_eps() { return 316.22776601683796f; }
     static __device__ __forceinline__ float c375() { return 0.375f; }
     static __device__ __forceinline__ float third() { return 0.5f / 1.5f; }
+    static __device__ __forceinline__ float sqrt_eps() { return 0.0031622776601683794f; }
 };
 
 // Branch-free 1/sqrt(x) and 1/x for well-scaled positive x (densities, gaps): hardware

@@ -238,9 +238,11 @@ __device__ __forceinline__ void aflux(const ARec<T>& L, const ARec<T>& R, T wr, 
     const T g = u0 - ueq0;
     const T y0 = r0 * g;
     // flux_prime at Q0 with r clamped at eps
-    const bool big = r0 >= DHTS_EPS_LIT;
-    const T inv_sq = big ? f_rcp(rootr) : DHTS_RSQRT_EPS_LIT;      // rootr >= sqrt(eps) where it is selected; a non-finite value in the other arm is discarded
-    const T rr = big ? r0 : DHTS_EPS_LIT;
+    // flux_prime at Q0 clamps r at eps: with rootc = sqrt(max(r0, eps)) both clamped quantities follow without a select on
+    // constants (1 / sqrt(max(r0, eps)) and max(r0, eps); at r0 < eps they differ from the literal 1 / sqrt(eps), eps by an ulp)
+    const T rootc = t_max(rootr, KC<T>::sqrt_eps());
+    const T inv_sq = f_rcp(rootc);
+    const T rr = rootc * rootc;
     const T ueqp0 = -k.hum * inv_sq;
     const T yr = y0 * (inv_sq * inv_sq);
     const T f00 = fma(rr, ueqp0, ueq0);
@@ -279,9 +281,11 @@ __device__ __forceinline__ void aflux_x(const ARec<T>& L, const ARec<T>& R, T wr
     const T ueq0 = fma(-k.umax, f_sqrt_pos(fma(root, root, DHTS_EPS_LIT)), k.umax);
     const T g = u0 - ueq0;
     const T y0 = r0 * g;
-    const bool big = r0 >= DHTS_EPS_LIT;
-    const T inv_sq = big ? f_rcp(rootr) : DHTS_RSQRT_EPS_LIT;
-    const T rr = big ? r0 : DHTS_EPS_LIT;
+    // flux_prime at Q0 clamps r at eps: with rootc = sqrt(max(r0, eps)) both clamped quantities follow without a select on
+    // constants (1 / sqrt(max(r0, eps)) and max(r0, eps); at r0 < eps they differ from the literal 1 / sqrt(eps), eps by an ulp)
+    const T rootc = t_max(rootr, KC<T>::sqrt_eps());
+    const T inv_sq = f_rcp(rootc);
+    const T rr = rootc * rootc;
     const T ueqp0 = -k.hum * inv_sq;
     const T yr = y0 * (inv_sq * inv_sq);
     const T f00 = fma(rr, ueqp0, ueq0);
