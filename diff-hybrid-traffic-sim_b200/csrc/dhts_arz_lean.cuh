@@ -308,14 +308,14 @@ __device__ __forceinline__ void aflux_x(const ARec<T>& L, const ARec<T>& R, T wr
     pbr = cB * (R.plr + R.ueqp);
     pby = cB * R.ri;
 }
-// the mailbox record of that path: 8 fields of the cell + its old adjoint
-constexpr int RF_ADJX = 10;
+// the mailbox record of that path: the 7 fields aflux_x reads of its LEFT cell + that cell's old adjoint
+constexpr int RF_ADJX = 9;
 template <typename T> __device__ __forceinline__ void pack_x(const ARec<T>& c, T gr, T gy, T* a) {
-    a[0] = c.us; a[1] = c.sq; a[2] = c.f00; a[3] = c.f10; a[4] = c.f11; a[5] = c.plr; a[6] = c.ri; a[7] = c.ueqp; a[8] = gr; a[9] = gy;
+    a[0] = c.us; a[1] = c.sq; a[2] = c.f00; a[3] = c.f10; a[4] = c.f11; a[5] = c.plr; a[6] = c.ri; a[7] = gr; a[8] = gy;
 }
 template <typename T> __device__ __forceinline__ ARec<T> unpack_x(const T* a) {
-    ARec<T> c; c.r = T(0); c.w = T(0);
-    c.us = a[0]; c.sq = a[1]; c.f00 = a[2]; c.f10 = a[3]; c.f11 = a[4]; c.plr = a[5]; c.ri = a[6]; c.ueqp = a[7];
+    ARec<T> c; c.r = T(0); c.w = T(0); c.ueqp = T(0);
+    c.us = a[0]; c.sq = a[1]; c.f00 = a[2]; c.f10 = a[3]; c.f11 = a[4]; c.plr = a[5]; c.ri = a[6];
     return c;
 }
 
