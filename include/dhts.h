@@ -132,6 +132,7 @@ int dhts_arz_rollout_fwd_f32(const float* r0, const float* y0, const float* u0, 
 /* Adjoint of the rollout: the chain of dMacroForwardLayer.backward calls autograd makes for the T steps
  * (road/lane/dmacro_lane.py:277-310), flux-difference form, no stored Jacobian band.
  *   ckpt                    what the forward call wrote (same ckpt_every, same ckpt_mode)
+ *   dx, umax / dx_all, umax_all  as in the forward call (both arrays, or both NULL with the two scalars)
  *   rT, yT                  final state (only read when g_uT is given: uT = compute_u(rT, yT))
  *   g_rT, g_yT, g_uT [B][N] adjoint of the final state, each may be NULL
  *   scratch                 dhts_arz_rollout_scratch_elems(B, N, ckpt_every) elements (0 when ckpt_every = 1)
