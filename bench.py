@@ -778,9 +778,10 @@ def run_ours(a):
             "phase_ms_per_step": {"arz_fwd": arz_fwd / K, "arz_bwd": arz_bwd / K, "arz_total": arz_all / K,
                                   "idm_fwd": idm_fwd / K, "idm_bwd": idm_bwd / K, "idm_total": idm_all / K},
             "gpu_launches": (2 * len(arz_chunks) + 2) * K,
+            # template arguments: cells per thread, register budget, adjoint mode, per-step inputs, stored outcomes, uniform geometry
             "roofline": {"kernel": "arz_rollout_bwd_reg_kernel<%s, 4, 2, %d, false, %s>" % (
                              "double" if a.dtype == "f64" else "float", 0 if arz_K == 1 else 2,
-                             "true" if dhts_b200.ops.arz_ckpt_elems(arz_chunk, N, T, arz_K, dt_t)[1] else "false"),
+                             "true, true" if dhts_b200.ops.arz_ckpt_elems(arz_chunk, N, T, arz_K, dt_t)[1] else "false, false"),
                          "bound": "hbm", "achieved": bwd_bytes / bwd_s / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": bwd_bytes / bwd_s / 1e9 / peak, "frac_is": "of_streaming_model",
                          "traffic": traffic, "traffic_source": pb.get("source"), "peak_source": peak_src,
