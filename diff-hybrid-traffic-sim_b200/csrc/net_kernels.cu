@@ -329,11 +329,16 @@ static int net_sm_count() {
     return n;
 }
 // Few replicas (latency-bound: a CTA's step time is what counts): one thread per interface, NC + L of them, up to 512.
-// Many replicas (throughput-bound: several CTAs per SM hide each other's barriers): half as many threads, each looping
-// twice, so that two CTAs of the 128-register adjoint fit an SM.
-static int net_threads(int L, int NC, int R) {
+// Many replicas (throughput-bound: several CTAs per SM hide each other's barriers): a fraction of that, each thread looping --
+// a third for the forward kernel (on the ITSCP grid 2 L = NC = 288 and NI = 432 are then 2, 2 and 3 nearly full iterations of
+// 160 threads: 16.1 instead of 17.9 ms at 2048 replicas, r3w), half for the adjoint (three 80-register CTAs per SM; a third
+// measured 43.2 instead of 41.5 ms).
+static int net_threads(int L, int NC, int R, bool adj) {
     int ni = NC + L;
-    if (R > net_sm_count()) ni = (ni + 1) / 2;
+    static const int divf = [] { const char* e = getenv("DHTS_NET_DIV_FWD"); const int d = e ? atoi(e) : 3; return d >= 1 && d <= 8 ? d : 3; }();
+    static const int divb = [] { const char* e = getenv("DHTS_NET_DIV_BWD"); const int d = e ? atoi(e) : 2; return d >= 1 && d <= 8 ? d : 2; }();
+    const int div = adj ? divb : divf;
+    if (R > net_sm_count()) ni = (ni + div - 1) / div;
     int t = (ni + 31) / 32 * 32;
     return t > 512 ? 512 : (t < 32 ? 32 : t);
 }
@@ -370,7 +375,7 @@ static int net_fwd(const NetArgs<T>& a, const T* r0, const T* y0, const T* u0, c
     if (rc) return rc;
     if (!r0 || !y0 || !u0 || !hist || !flags || (a.n_own > 0 && (!own0 || !ownh))) return DHTS_ERR_INVALID;
     if (a.R == 0) return DHTS_OK;
-    const int threads = net_threads(a.L, a.NC, a.R);
+    const int threads = net_threads(a.L, a.NC, a.R, false);
     const size_t smem = net_smem<T>(a.L, a.NC, a.n_own, false, threads);
     int grid = 1;
     rc = net_launch_cfg<T>(net_rollout_fwd_kernel<T>, smem, threads, a.R, &grid);
@@ -386,7 +391,7 @@ static int net_bwd(const NetArgs<T>& a, const T* hist, const T* ownh, const T* g
     if (rc) return rc;
     if (!hist || !g_r0 || !g_y0 || !g_u0 || !flags || (a.n_own > 0 && !ownh)) return DHTS_ERR_INVALID;
     if (a.R == 0) return DHTS_OK;
-    const int threads = net_threads(a.L, a.NC, a.R);
+    const int threads = net_threads(a.L, a.NC, a.R, true);
     const size_t smem = net_smem<T>(a.L, a.NC, a.n_own, true, threads);
     int grid = 1;
     static const bool occ3 = [] { const char* e = getenv("DHTS_NET_BWD_MINB"); return !e || atoi(e) != 1; }();
