@@ -46,3 +46,25 @@ def test_product_package_never_touches_the_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.lower() or f == "_lib.py" and "oracle" not in txt, (dirpath, f)
                 assert "/root/reference" not in txt, (dirpath, f)
+
+
+def test_ckpt_size_query_is_host_side_and_matches_the_documented_layout():
+    """dhts_arz_rollout_ckpt_elems_* (include/dhts.h) plans on the host: the S stored states [S][2][B][N] and, in ckpt_mode 1
+    (every state stored, whole warps per lane), N / 4 bytes of interface-outcome ballots per lane and step behind them."""
+    import dhts_b200
+    lib = ctypes.CDLL(dhts_b200.build())
+    f = lib.dhts_arz_rollout_ckpt_elems_f64
+    f.restype = ctypes.c_longlong
+    mode = ctypes.c_int(-1)
+    B, N, T = 6560, 1024, 1000
+    n = f(B, N, T, 1, ctypes.byref(mode))
+    assert mode.value == 1 and n == T * 2 * B * N + T * B * (N // 4) // 8        # the bench's lane chunk
+    n = f(B, N, T, 32, ctypes.byref(mode))
+    assert mode.value == 0 and n == ((T + 31) // 32) * 2 * B * N                  # sparse checkpoints: states only
+    n = f(37, 10, 60, 1, ctypes.byref(mode))
+    assert mode.value == 0 and n == 60 * 2 * 37 * 10                              # one cell per thread: no outcome storage
+    g = lib.dhts_arz_rollout_ckpt_elems_f32
+    g.restype = ctypes.c_longlong
+    n = g(8, 1024, 10, 1, ctypes.byref(mode))
+    assert mode.value == 1 and n == 10 * 2 * 8 * 1024 + 10 * 8 * (1024 // 4) // 4
+    assert f(-1, 8, 1, 1, ctypes.byref(mode)) < 0
