@@ -125,3 +125,39 @@ def test_two_rank_trainer_matches_single_process(tmp_path):
         assert max(abs(a - b) for a, b in zip(head, single[2])) < 1e-5
         assert abs(total - single[3]) < 1e-4 * max(1.0, abs(single[3]))
     assert os.path.exists(os.path.join(str(tmp_path), "ws2", "eval.txt"))           # rank 0 alone writes the logs
+
+
+def test_bench_inputs_do_not_depend_on_the_number_of_ranks():
+    """bench.py's strong split: a lane's synthetic inputs are a function of (batch seed, global lane index) only, so N ranks
+    working on contiguous lane blocks of ONE batch see exactly the rows of the unsharded batch (what
+    `shard_equals_unshard_bitwise` then checks on the device results)."""
+    import sys
+    import types
+    sys.path.insert(0, ROOT)
+    import bench
+    from dhts_b200 import dist
+    a = types.SimpleNamespace(lanes=37, cells=16, micro_lanes=29, lane_vehicles=5, sim_steps=10)
+    full = bench.make_arz_inputs(a, 0, torch)
+    fidm = bench.make_idm_inputs(a, 0, torch)
+    for ws in (2, 3, 8):
+        rows = {k: [] for k in ("r0", "u0", "gr", "gu", "tr", "tu")}
+        veh = {k: [] for k in ("p0", "v0", "tp", "tv")}
+        par = []
+        for r in range(ws):
+            lo, hi = dist.shard_range(a.lanes, r, ws)
+            part = bench.make_arz_inputs(a, 0, torch, lo, hi)
+            for k in rows:
+                rows[k].append(part[k])
+            lo, hi = dist.shard_range(a.micro_lanes, r, ws)
+            pi = bench.make_idm_inputs(a, 0, torch, lo, hi)
+            assert pi["off"].tolist() == [i * a.lane_vehicles for i in range(hi - lo + 1)]
+            for k in veh:
+                veh[k].append(pi[k])
+            par.append(pi["params"])
+        for k in rows:
+            assert torch.equal(torch.cat(rows[k]), full[k]), (ws, k)
+        for k in veh:
+            assert torch.equal(torch.cat(veh[k]), fidm[k]), (ws, k)
+        assert torch.equal(torch.cat(par, dim=1), fidm["params"])
+    # a different batch seed (the weak split: one batch per rank) gives different lanes
+    assert not torch.equal(bench.make_arz_inputs(a, 1, torch)["r0"], full["r0"])
