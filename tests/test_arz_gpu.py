@@ -107,6 +107,29 @@ def test_rollout_vs_golden_fp64(dev, ckpt_every):
     assert relerr(gg, g["g_ghost"]) < 1e-8
 
 
+@pytest.mark.parametrize("ckpt_every", [1, 8])
+def test_rollout_with_vacuum_vs_live_reference(dev, ckpt_every):
+    """The live reference's own rollout over lanes with empty and near-vacuum stretches and vacuum ghosts (fixture
+    arz_rollout_vac_fp64, oracle/gen_golden_vac.py): 128-cell lanes, so ckpt_every = 1 runs the staged forward kernel with
+    stored outcomes and the ring adjoint (four cells per thread, vacuum votes), ckpt_every = 8 the recompute path."""
+    import dhts_b200
+    from dhts_b200 import functional as F
+    g = golden("arz_rollout_vac_fp64")
+    T = int(g["T"])
+    flags = dhts_b200.Flags(dev)
+    r0 = T64(g["r0"], dev).requires_grad_(); u0 = T64(g["u0"], dev).requires_grad_()
+    gr = T64(g["ghost_ru"][:, :, 0], dev).requires_grad_(); gu = T64(g["ghost_ru"][:, :, 1], dev).requires_grad_()
+    rT, yT, uT = F.arz_rollout(r0, u0, gr, gu, float(g["dx"]), float(g["umax"]), float(g["dt"]), T,
+                               ckpt_every=ckpt_every, flags=flags)
+    ((rT * T64(g["w_r"], dev)).sum() + (uT * T64(g["w_u"], dev)).sum()).backward()
+    flags.check()
+    assert (g["rT"] < 1e-5).any()
+    assert relerr(rT.detach().cpu(), g["rT"]) < 1e-9 and relerr(yT.detach().cpu(), g["yT"]) < 1e-9
+    assert relerr(uT.detach().cpu(), g["uT"]) < 1e-9
+    assert relerr(r0.grad.cpu(), g["g_r0"]) < 1e-8 and relerr(u0.grad.cpu(), g["g_u0"]) < 1e-8
+    assert relerr(torch.stack([gr.grad, gu.grad], -1).cpu(), g["g_ghost"]) < 1e-8
+
+
 def test_rollout_vs_golden_fp32(dev):
     """fp32 build vs the reference as shipped, T=300: states 1e-4, gradients 2e-3 of the largest entry."""
     import dhts_b200

@@ -44,6 +44,19 @@ def test_arz_rollout(tier, f32, tol_s, tol_g):
         assert relerr(o[a], g[a]) < tol_g, a
 
 
+def test_arz_rollout_with_vacuum():
+    """Lanes with empty / near-vacuum stretches and vacuum ghosts, 60 steps of the live reference (oracle/gen_golden_vac.py):
+    the vacuum branches of the case tree and the below-eps fix-ups of u_eq / flux_prime in the oracle's rollout and adjoint."""
+    g = golden("arz_rollout_vac_fp64")
+    o = O.arz_rollout(g["r0"], g["u0"], g["ghost_ru"], float(g["dx"]), float(g["umax"]), float(g["dt"]), int(g["T"]),
+                      g_rT=g["w_r"], g_uT=g["w_u"])
+    assert o["cfl"] == 0 and (g["rT"] < 1e-5).any() and (g["r0"] == 0).any()
+    for a in ("rT", "yT", "uT"):
+        assert relerr(o[a], g[a]) < 1e-12, a
+    for a in ("g_r0", "g_u0", "g_ghost"):
+        assert relerr(o[a], g[a]) < 1e-11, a
+
+
 @pytest.mark.parametrize("tier,f32,tol_s,tol_g", TIERS)
 def test_idm_step(tier, f32, tol_s, tol_g):
     g = golden("idm_step_" + tier)
